@@ -1,0 +1,176 @@
+/*
+ * phylign_cuda.h -- C ABI of libphylign_cuda.so (sm_100a), the drop-in boundary
+ * for Phylign's match stage.
+ *
+ * What it replaces in the reference (file:line under /root/reference):
+ *   scripts/run_cobs_streaming.sh:24-29, Snakefile:419-424, Snakefile:476-481
+ *       `cobs query --load-complete -t THR -T N -i INDEX -f QUERIES`   -> phy_index_* + phy_match
+ *   scripts/postprocess_cobs.py:21-38   per-batch top-N + ties          -> phy_match (top_n)
+ *   scripts/filter_queries.py:105-156   global top-N + ties over batches -> phy_merge_topn
+ *
+ * Conventions: plain pointers and sizes only; every function returns PHY_OK (0)
+ * or a negative status and leaves a message retrievable with phy_last_error();
+ * buffers passed in are caller-owned and may be reused as soon as the call
+ * returns; buffers handed out (phy_results*, phy_merged*) are owned by the
+ * library and released only with phy_results_free / phy_merged_free.
+ * One phy_ctx drives ONE GPU from one host thread (one process per GPU; the
+ * multi-GPU exchange goes through phy_nccl_*).  There is no CPU fallback: every
+ * compute entry point fails with PHY_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef PHYLIGN_CUDA_H
+#define PHYLIGN_CUDA_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PHY_OK 0
+#define PHY_ERR_CUDA (-1)   /* CUDA runtime / no device */
+#define PHY_ERR_ARG (-2)    /* invalid argument */
+#define PHY_ERR_NOMEM (-3)  /* HBM budget or host memory exhausted */
+#define PHY_ERR_STATE (-4)  /* call out of order (e.g. match before queries) */
+#define PHY_ERR_NCCL (-5)   /* NCCL failure / libnccl not loadable */
+#define PHY_ERR_QUERY (-6)  /* query holds a letter outside ACGT (cobs aborts too) */
+
+#define PHY_ABI_VERSION 1
+
+typedef struct phy_ctx phy_ctx;
+
+int phy_abi_version(void);
+/* number of visible CUDA devices (0 and PHY_ERR_CUDA when none) */
+int phy_device_count(int* n);
+/* hbm_budget = 0 -> use what cudaMemGetInfo reports free, minus a safety margin */
+int phy_ctx_create(phy_ctx** out, int device, uint64_t hbm_budget);
+void phy_ctx_destroy(phy_ctx* ctx);
+/* ctx may be NULL: returns the message of the last failed call without a ctx */
+const char* phy_last_error(const phy_ctx* ctx);
+
+/* ------------------------------------------------------------------ index store
+ * A COBS classic index is streamed in as the packed body
+ * bytes (signature_size rows of ceil(n_docs/8) bytes, file order); the library
+ * stages through its own pinned ring and re-strides rows on the device.  Header
+ * parsing and document names stay with the caller. */
+int phy_index_begin(phy_ctx* ctx, const char* batch_name, uint32_t term_size,
+                    uint8_t canonicalize, uint64_t signature_size, uint64_t num_hashes,
+                    uint32_t n_docs, int* idx_id);
+int phy_index_push(phy_ctx* ctx, int idx_id, const void* host_chunk, uint64_t nbytes);
+/* fails with PHY_ERR_STATE unless exactly signature_size*row_size bytes arrived */
+int phy_index_commit(phy_ctx* ctx, int idx_id);
+int phy_index_evict(phy_ctx* ctx, int idx_id);
+/* sort ranks used by the merge key (-score, batch, ref) of filter_queries.py:135:
+ * batch_rank = rank of the batch name among ALL batches of the job (global across
+ * GPUs, < 4096), ref_rank[d] = rank of document d's accession inside the batch.
+ * Defaults: batch_rank = idx_id, ref_rank[d] = d. */
+int phy_index_set_ranks(phy_ctx* ctx, int idx_id, uint32_t batch_rank,
+                        const uint32_t* ref_rank);
+
+typedef struct phy_index_info {
+    uint64_t signature_size, num_hashes, hbm_bytes;
+    uint32_t term_size, n_docs, row_size, row_stride, batch_rank;
+    uint8_t canonicalize, committed;
+} phy_index_info;
+int phy_index_info_get(phy_ctx* ctx, int idx_id, phy_index_info* out);
+int phy_index_count(phy_ctx* ctx, int* n_resident);
+/* packed body bytes back to the host (tests, cache files) */
+int phy_index_download(phy_ctx* ctx, int idx_id, void* host_out, uint64_t nbytes);
+
+/* --------------------------------------------------------------------- queries
+ * seq_concat: ASCII bases of all queries back to back (upper-case ACGT only,
+ * the contract of intermediate/01_queries_merged, Snakefile:326-332);
+ * offs[nq+1]: start of each query in seq_concat.  Copies host -> HBM. */
+int phy_queries_set(phy_ctx* ctx, const char* seq_concat, const uint64_t* offs, uint32_t nq);
+
+/* ----------------------------------------------------------------------- match */
+typedef struct phy_match_params {
+    double threshold;     /* cobs -t : doc reported iff score >= threshold*K */
+    uint32_t top_n;       /* postprocess_cobs.py -n : keep N best + ties per (query,index); 0 = keep all */
+    uint32_t floor_mode;  /* 0: T=ceil(t*K) (default)  1: T=floor(t*K)  (SURVEY A.6 switch) */
+} phy_match_params;
+
+typedef struct phy_hit { uint32_t doc; uint32_t score; } phy_hit;
+/* one non-empty (query, index) block of the cobs output */
+typedef struct phy_unit {
+    uint32_t query;    /* position in phy_queries_set order */
+    uint32_t index;    /* idx_id */
+    uint32_t n_pass;   /* docs with score >= T (the header count, before top-N) */
+    uint32_t n_kept;   /* hits stored: N best + ties */
+    uint64_t offset;   /* first hit in phy_results.hits */
+} phy_unit;
+
+typedef struct phy_results {
+    uint32_t n_queries, n_indexes;
+    uint64_t n_units;      /* sorted by (index, query); absent pairs have 0 hits */
+    phy_unit* units;
+    uint64_t n_hits;
+    phy_hit* hits;         /* per unit sorted by (score desc, doc asc) */
+    const uint32_t* n_kmers;   /* [n_queries] K = max(L-k+1, 0) */
+    uint64_t h2d_bytes, d2h_bytes;
+} phy_results;
+
+/* device-only part: hash + gather/count + threshold/top-N (+ local merge when
+ * merge_top_n > 0) for the queries set last, against all committed indexes.
+ * Results stay in HBM until phy_results_fetch / phy_merged_fetch. */
+int phy_match_run(phy_ctx* ctx, const phy_match_params* p, uint32_t merge_top_n);
+int phy_results_fetch(phy_ctx* ctx, phy_results** out);
+void phy_results_free(phy_results* r);
+/* convenience: phy_match_run + phy_results_fetch */
+int phy_match(phy_ctx* ctx, const phy_match_params* p, phy_results** out);
+
+/* dense score matrix of ONE index for the queries set last: scores[nq*n_docs]
+ * (uint32, row = query).  Verification / `bit-exact scores` entry point. */
+int phy_scores(phy_ctx* ctx, int idx_id, uint32_t* host_scores);
+
+/* ----------------------------------------------------------------------- merge
+ * filter_queries.py semantics over all indexes of all GPUs: per query every
+ * candidate whose score >= the N-th largest score, ordered by
+ * (score desc, batch_rank asc, ref_rank asc). */
+typedef struct phy_cand { uint32_t score; uint32_t batch_rank; uint32_t doc; uint32_t ref_rank; } phy_cand;
+typedef struct phy_merged {
+    uint32_t n_queries;
+    uint64_t* offs;       /* [n_queries+1] */
+    phy_cand* cands;
+    uint64_t d2h_bytes;
+} phy_merged;
+/* needs phy_match_run(..., merge_top_n > 0) before.  With NCCL initialised the
+ * per-GPU lists are gathered over NVLink and merged on rank 0 (other ranks get
+ * an empty list with n_queries set). */
+int phy_merged_fetch(phy_ctx* ctx, phy_merged** out);
+void phy_merged_free(phy_merged* m);
+
+/* ------------------------------------------------------------------- multi-GPU */
+#define PHY_NCCL_ID_BYTES 128
+int phy_nccl_unique_id(void* id_out /* PHY_NCCL_ID_BYTES */);
+int phy_nccl_init(phy_ctx* ctx, const void* id, int rank, int n_ranks);
+
+/* -------------------------------------------------------------------- timing
+ * CUDA-event timer on the stream every kernel of this ctx is launched on. */
+int phy_timer_start(phy_ctx* ctx);
+int phy_timer_stop(phy_ctx* ctx, float* ms);
+int phy_sync(phy_ctx* ctx);
+/* per-phase device times (ms) of the last phy_match_run:
+ * [0] hash  [1] gather+count(+select)  [2] sort/merge  [3] launches of own kernels */
+int phy_last_phase_ms(phy_ctx* ctx, float out[4]);
+/* write a buffer larger than L2 (bench hygiene between timed iterations) */
+int phy_flush_l2(phy_ctx* ctx);
+
+/* ---------------------------------------------- synthetic workload (bench/tests)
+ * Spec v1, restated independently in oracle/cobs_oracle.c (tests check byte
+ * equality).  Builds an index on the device from procedural genomes
+ * (`cobs classic-construct` shape: every k-mer of every document sets its bit). */
+typedef struct phy_synth_spec {
+    uint64_t seed;
+    uint32_t n_docs, genome_len, clade_size, clade_sub_q16, doc_sub_q16;
+} phy_synth_spec;
+/* index must have been phy_index_begin()'d; fills and commits it */
+int phy_index_synth(phy_ctx* ctx, int idx_id, const phy_synth_spec* spec);
+/* n_reads reads of read_len bases into host_out (n_reads*read_len ASCII bytes) */
+int phy_synth_reads(phy_ctx* ctx, const phy_synth_spec* specs, uint32_t n_specs,
+                    uint64_t reads_seed, uint64_t first_read, uint32_t n_reads,
+                    uint32_t read_len, uint32_t random_q8, uint32_t err_q16, char* host_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,583 @@
+// gather_count.cu -- K2/K3: the hot kernel of the match stage.
+//
+// Replaces cobs `read_from_disk` (row gather) + AND across hash functions +
+// `compute_counts` (SSE2 byte-expansion adds) + `counts_to_result` (threshold), and the
+// per-batch top-N + ties of /root/reference/scripts/postprocess_cobs.py:21-38
+// (Appendix A.4-A.7).
+//
+// Shape of the work: for every (query, index) and every query k-mer, one row of the
+// bit-sliced index (ceil(D/8) bytes, random address) is read from HBM and added into D
+// per-document counters.  HBM-bound: one 128-bit load per lane per row chunk, and the
+// counters are VERTICAL (bit-sliced): plane p of a lane holds bit p of the counters of
+// the 128 documents that lane owns, so adding a row costs ~3.5 LOP3 per 32 documents
+// (Harley-Seal carry-save over blocks of 8 rows, then a ripple into the upper planes)
+// instead of one add per document.  Threshold and top-N cut are evaluated bit-sliced on
+// the planes; only passing documents ever get their score extracted.
+//
+// Geometry: a row is covered by LPR lanes x 16 B (LPR = 1..32, a power of two chosen
+// from the row stride); a warp holds 32/LPR independent (query,index) units.
+#include "phy_internal.cuh"
+
+#include <algorithm>
+#include <cmath>
+
+namespace {
+
+constexpr unsigned FULL = 0xFFFFFFFFu;
+
+__device__ __forceinline__ uint4 ldg_row16(const uint8_t* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p));
+    return v;
+}
+
+// full adder on 32 documents at once: 2 LOP3
+__device__ __forceinline__ void csa(uint32_t& hi, uint32_t& lo, uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t u = a ^ b;
+    hi = (a & b) | (u & c);
+    lo = u ^ c;
+}
+
+template <int LPR>
+__device__ __forceinline__ unsigned group_mask(int lane) {
+    if constexpr (LPR == 32) return FULL;
+    else return ((1u << LPR) - 1u) << (lane & ~(LPR - 1));
+}
+template <int LPR>
+__device__ __forceinline__ uint32_t group_sum(uint32_t v, unsigned gm) {
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gm, v, o);
+    return v;
+}
+template <int LPR>
+__device__ __forceinline__ uint32_t group_exscan(uint32_t v, unsigned gm, int col) {
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < LPR; o <<= 1) {
+        uint32_t t = __shfl_up_sync(gm, incl, o, LPR);
+        if (col >= o) incl += t;
+    }
+    return incl - v;
+}
+
+// documents (bits) whose vertical counter is >= T
+template <int P>
+__device__ __forceinline__ uint32_t ge_mask(const uint32_t (&pl)[P][4], int w, uint32_t T) {
+    uint32_t gt = 0, eq = FULL;
+#pragma unroll
+    for (int p = P - 1; p >= 0; p--) {
+        uint32_t c = pl[p][w];
+        if ((T >> p) & 1u) {
+            eq &= c;
+        } else {
+            gt |= eq & c;
+            eq &= ~c;
+        }
+    }
+    return gt | eq;
+}
+
+template <int P>
+__device__ __forceinline__ uint32_t extract_score(const uint32_t (&pl)[P][4], int w, int b) {
+    uint32_t s = 0;
+#pragma unroll
+    for (int p = 0; p < P; p++) {
+        uint32_t x = w == 0 ? pl[p][0] : (w == 1 ? pl[p][1] : (w == 2 ? pl[p][2] : pl[p][3]));
+        s |= ((x >> b) & 1u) << p;
+    }
+    return s;
+}
+
+// Add `nrows` index rows (one per query k-mer, AND-ed over the hash functions) into the
+// vertical counters of this lane.  colbase = rows + chunk offset + col*16.
+template <int LPR, int P>
+__device__ __forceinline__ void accumulate(uint32_t (&pl)[P][4], const uint8_t* __restrict__ colbase,
+                                           bool lane_on, uint32_t stride, uint64_t sig,
+                                           uint64_t magic, uint32_t num_hashes,
+                                           const uint64_t* __restrict__ hq, uint64_t hstride,
+                                           uint32_t nrows, int lane, unsigned gm) {
+    constexpr int HB = LPR >= 8 ? LPR : 8;  // rows whose hashes are fetched per outer step
+    constexpr int NH = HB / LPR;            // hashes fetched per lane per outer step
+    const int col = lane & (LPR - 1);
+    const int gbase = lane - col;
+    for (uint32_t base = 0; base < nrows; base += HB) {
+        uint32_t myrow[NH];
+#pragma unroll
+        for (int t = 0; t < NH; t++) {
+            uint32_t hidx = base + col + t * LPR;
+            myrow[t] = hidx < nrows ? phy_fastmod(__ldg(hq + hidx), sig, magic) : PHY_ROW_INVALID;
+        }
+#pragma unroll
+        for (int s = 0; s < HB / 8; s++) {
+            if (base + s * 8 >= nrows) break;  // uniform inside the group
+            uint4 v[8];
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                const int src = LPR >= 8 ? gbase + s * 8 + r : gbase + (r % LPR);
+                const int slot = LPR >= 8 ? 0 : r / LPR;
+                uint32_t rr = __shfl_sync(gm, myrow[slot], src);
+                if (rr != PHY_ROW_INVALID && lane_on) v[r] = ldg_row16(colbase + (uint64_t)rr * stride);
+                else v[r] = make_uint4(0, 0, 0, 0);
+            }
+            for (uint32_t j = 1; j < num_hashes; j++) {  // AND with the other hash functions' rows
+                uint32_t hidx = base + s * 8 + (LPR >= 8 ? (col & 7) : 0);
+                uint32_t mr[NH];
+#pragma unroll
+                for (int t = 0; t < NH; t++) {
+                    uint32_t hi2 = LPR >= 8 ? hidx : base + col + t * LPR;
+                    mr[t] = hi2 < nrows ? phy_fastmod(__ldg(hq + j * hstride + hi2), sig, magic) : PHY_ROW_INVALID;
+                }
+#pragma unroll
+                for (int r = 0; r < 8; r++) {
+                    const int src = LPR >= 8 ? gbase + r : gbase + (r % LPR);
+                    const int slot = LPR >= 8 ? 0 : r / LPR;
+                    uint32_t rr = __shfl_sync(gm, mr[slot], src);
+                    if (rr != PHY_ROW_INVALID && lane_on) {
+                        uint4 x = ldg_row16(colbase + (uint64_t)rr * stride);
+                        v[r].x &= x.x; v[r].y &= x.y; v[r].z &= x.z; v[r].w &= x.w;
+                    }
+                }
+            }
+#pragma unroll
+            for (int w = 0; w < 4; w++) {
+                auto W = [&](const uint4& q) -> uint32_t {
+                    return w == 0 ? q.x : (w == 1 ? q.y : (w == 2 ? q.z : q.w));
+                };
+                uint32_t twoA, twoB, fourA, fourB, eight;
+                csa(twoA, pl[0][w], pl[0][w], W(v[0]), W(v[1]));
+                csa(twoB, pl[0][w], pl[0][w], W(v[2]), W(v[3]));
+                csa(fourA, pl[1][w], pl[1][w], twoA, twoB);
+                csa(twoA, pl[0][w], pl[0][w], W(v[4]), W(v[5]));
+                csa(twoB, pl[0][w], pl[0][w], W(v[6]), W(v[7]));
+                csa(fourB, pl[1][w], pl[1][w], twoA, twoB);
+                csa(eight, pl[2][w], pl[2][w], fourA, fourB);
+                uint32_t carry = eight;
+#pragma unroll
+                for (int p = 3; p < P; p++) {
+                    uint32_t t = pl[p][w] & carry;
+                    pl[p][w] ^= carry;
+                    carry = t;
+                }
+            }
+        }
+    }
+}
+
+struct GatherArgs {
+    const DevIndex* indexes;
+    const uint32_t* class_idx;  // index ids handled by this launch (same LPR class)
+    uint32_t n_class_idx;
+    const uint32_t* qlist;      // query ids with 1 <= K <= PHY_FUSED_KMAX
+    uint32_t n_q;
+    const uint64_t* koffs;
+    const uint32_t* nk;
+    const uint32_t* T;
+    const uint64_t* hashes;
+    uint64_t total_kmers;
+    uint32_t top_n;
+    phy_unit* units;
+    uint64_t units_cap;
+    phy_hit* hits;
+    uint64_t hits_cap;
+    unsigned long long* counters;  // [0] hits cursor, [1] units cursor
+    uint32_t* qcount;
+};
+
+// Fused path: one group of LPR lanes = one (query, index) unit, whole query, whole row.
+template <int LPR>
+__global__ void __launch_bounds__(256, 2) gather_count_fused_kernel(const GatherArgs a) {
+    constexpr int P = PHY_FUSED_PLANES;
+    constexpr int G = 32 / LPR;
+    const int lane = threadIdx.x & 31;
+    const int col = lane & (LPR - 1);
+    const unsigned gm = group_mask<LPR>(lane);
+    const uint64_t warp = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint64_t gid = warp * G + (lane / LPR);
+    const uint64_t total = (uint64_t)a.n_class_idx * a.n_q;
+    if (gid >= total) return;  // whole groups leave together
+    const uint32_t ipos = (uint32_t)(gid / a.n_q);
+    const uint32_t q = a.qlist[gid - (uint64_t)ipos * a.n_q];
+    const DevIndex& ix = a.indexes[a.class_idx[ipos]];
+    const uint32_t stride = ix.stride, n_docs = ix.n_docs;
+    const uint32_t nrows = a.nk[q];
+
+    uint32_t pl[P][4];
+#pragma unroll
+    for (int p = 0; p < P; p++) pl[p][0] = pl[p][1] = pl[p][2] = pl[p][3] = 0;
+
+    accumulate<LPR, P>(pl, ix.rows + col * 16, (uint32_t)col * 16 < stride, stride, ix.sig, ix.magic,
+                       ix.num_hashes, a.hashes + a.koffs[q], a.total_kmers, nrows, lane, gm);
+
+    // ---- threshold (cobs counts_to_result): score >= T, bit-sliced
+    const uint32_t T = a.T[q];
+    const uint32_t doc0 = (uint32_t)col * 128u;
+    uint32_t pass[4], cnt = 0;
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+        uint32_t d = doc0 + w * 32u;
+        uint32_t valid = d >= n_docs ? 0u : (n_docs - d >= 32u ? FULL : ((1u << (n_docs - d)) - 1u));
+        pass[w] = T > nrows ? 0u : (ge_mask<P>(pl, w, T) & valid);
+        cnt += __popc(pass[w]);
+    }
+    const uint32_t n_pass = group_sum<LPR>(cnt, gm);
+    if (n_pass == 0) return;
+
+    // ---- top-N + ties (postprocess_cobs.py:21-38): cut = N-th largest score
+    uint32_t n_kept = n_pass;
+    if (a.top_n != 0 && n_pass > a.top_n) {
+        uint32_t cut = 0;
+#pragma unroll
+        for (int p = P - 1; p >= 0; p--) {
+            uint32_t cand = cut | (1u << p), c = 0;
+#pragma unroll
+            for (int w = 0; w < 4; w++) c += __popc(ge_mask<P>(pl, w, cand) & pass[w]);
+            c = group_sum<LPR>(c, gm);
+            if (c >= a.top_n) cut = cand;
+        }
+        cnt = 0;
+#pragma unroll
+        for (int w = 0; w < 4; w++) {
+            pass[w] &= ge_mask<P>(pl, w, cut);
+            cnt += __popc(pass[w]);
+        }
+        n_kept = group_sum<LPR>(cnt, gm);
+    }
+
+    // ---- emit (doc ascending inside the unit; sorted by score later)
+    const uint32_t ex = group_exscan<LPR>(cnt, gm, col);
+    unsigned long long off = 0;
+    if (col == 0) {
+        off = atomicAdd(&a.counters[0], (unsigned long long)n_kept);
+        unsigned long long u = atomicAdd(&a.counters[1], 1ULL);
+        if (u < a.units_cap) {
+            phy_unit pu;
+            pu.query = q; pu.index = ix.idx_id; pu.n_pass = n_pass; pu.n_kept = n_kept; pu.offset = off;
+            a.units[u] = pu;
+        }
+        atomicAdd(&a.qcount[q], n_kept);
+    }
+    off = __shfl_sync(gm, off, lane - col);
+    if (off + n_kept > a.hits_cap) return;  // host regrows and reruns
+    phy_hit* out = a.hits + off + ex;
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+        uint32_t m = pass[w];
+        while (m) {
+            int b = __ffs(m) - 1;
+            m &= m - 1;
+            phy_hit h;
+            h.doc = doc0 + w * 32 + b;
+            h.score = extract_score<P>(pl, w, b);
+            *out++ = h;
+        }
+    }
+}
+
+// General path: k-mers [k0,k1) of a query against ONE index and one 512-B column chunk,
+// flushed into a dense uint32 score row.  Used for queries with K > PHY_FUSED_KMAX, for
+// rows wider than 512 B (D > 4096) and by phy_scores().
+template <int LPR>
+__global__ void __launch_bounds__(256, 2) accum_scores_kernel(
+    const DevIndex* __restrict__ ixp, const SlowItem* __restrict__ items, uint32_t n_items,
+    uint32_t n_chunks, const uint64_t* __restrict__ koffs, const uint64_t* __restrict__ hashes,
+    uint64_t total_kmers, uint32_t* __restrict__ scores) {
+    constexpr int P = PHY_FUSED_PLANES;
+    constexpr int G = 32 / LPR;
+    const int lane = threadIdx.x & 31;
+    const int col = lane & (LPR - 1);
+    const unsigned gm = group_mask<LPR>(lane);
+    const uint64_t warp = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint64_t gid = warp * G + (lane / LPR);
+    if (gid >= (uint64_t)n_items * n_chunks) return;
+    const SlowItem it = items[gid / n_chunks];
+    const uint32_t chunk = (uint32_t)(gid % n_chunks);
+    const DevIndex& ix = *ixp;
+    const uint32_t stride = ix.stride, n_docs = ix.n_docs;
+    const uint32_t byte0 = chunk * PHY_CHUNK_BYTES + (uint32_t)col * 16u;
+
+    uint32_t pl[P][4];
+#pragma unroll
+    for (int p = 0; p < P; p++) pl[p][0] = pl[p][1] = pl[p][2] = pl[p][3] = 0;
+    accumulate<LPR, P>(pl, ix.rows + byte0, byte0 < stride, stride, ix.sig, ix.magic, ix.num_hashes,
+                       hashes + koffs[it.query] + it.k0, total_kmers, it.k1 - it.k0, lane, gm);
+    uint32_t* row = scores + (uint64_t)it.slot * n_docs;
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+        uint32_t any = 0;
+#pragma unroll
+        for (int p = 0; p < P; p++) any |= pl[p][w];
+        const uint32_t d0 = byte0 * 8u + w * 32u;
+        while (any) {
+            int b = __ffs(any) - 1;
+            any &= any - 1;
+            if (d0 + b < n_docs) atomicAdd(&row[d0 + b], extract_score<P>(pl, w, b));
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t block_sum(uint32_t v, uint32_t* sm) {
+    // all 256 threads; returns the total to every thread
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    __syncthreads();
+    if (lane == 0) sm[wid] = v;
+    __syncthreads();
+    uint32_t t = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) t += sm[i];
+    return t;
+}
+
+// threshold + top-N + ties on a dense score row (general path).  One block per slot.
+__global__ void __launch_bounds__(256) select_scores_kernel(
+    const uint32_t* __restrict__ scores, uint32_t n_docs, const uint32_t* __restrict__ slotq,
+    const uint32_t* __restrict__ Tq, const uint32_t* __restrict__ nk, uint32_t top_n,
+    uint32_t idx_id, phy_unit* units, uint64_t units_cap, phy_hit* hits, uint64_t hits_cap,
+    unsigned long long* counters, uint32_t* qcount) {
+    __shared__ uint32_t sm[8];
+    __shared__ uint32_t sm_scan[256];
+    __shared__ unsigned long long sm_off;
+    const uint32_t slot = blockIdx.x, q = slotq[slot];
+    const uint32_t* sc = scores + (uint64_t)slot * n_docs;
+    const uint32_t T = Tq[q], K = nk[q];
+    const uint32_t per = (n_docs + 255) / 256;
+    const uint32_t d_lo = min(threadIdx.x * per, n_docs), d_hi = min(d_lo + per, n_docs);
+    auto count_ge = [&](uint32_t c) {
+        uint32_t n = 0;
+        for (uint32_t d = threadIdx.x; d < n_docs; d += 256) n += sc[d] >= c;
+        return block_sum(n, sm);
+    };
+    const uint32_t n_pass = T > K ? 0 : count_ge(T);
+    if (n_pass == 0) return;
+    uint32_t cut = T, n_kept = n_pass;
+    if (top_n != 0 && n_pass > top_n) {
+        uint32_t lo = T, hi = K + 1;  // count_ge(lo) >= top_n, count_ge(hi) = 0
+        while (hi - lo > 1) {
+            uint32_t mid = lo + (hi - lo) / 2;
+            if (count_ge(mid) >= top_n) lo = mid; else hi = mid;
+        }
+        cut = lo;
+        n_kept = count_ge(cut);
+    }
+    uint32_t mine = 0;
+    for (uint32_t d = d_lo; d < d_hi; d++) mine += sc[d] >= cut;
+    sm_scan[threadIdx.x] = mine;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (int i = 0; i < 256; i++) { uint32_t t = sm_scan[i]; sm_scan[i] = run; run += t; }
+        unsigned long long off = atomicAdd(&counters[0], (unsigned long long)n_kept);
+        unsigned long long u = atomicAdd(&counters[1], 1ULL);
+        if (u < units_cap) {
+            phy_unit pu;
+            pu.query = q; pu.index = idx_id; pu.n_pass = n_pass; pu.n_kept = n_kept; pu.offset = off;
+            units[u] = pu;
+        }
+        atomicAdd(&qcount[q], n_kept);
+        sm_off = off;
+    }
+    __syncthreads();
+    if (sm_off + n_kept > hits_cap) return;
+    phy_hit* out = hits + sm_off + sm_scan[threadIdx.x];
+    for (uint32_t d = d_lo; d < d_hi; d++) {
+        uint32_t s = sc[d];
+        if (s >= cut) { phy_hit h; h.doc = d; h.score = s; *out++ = h; }
+    }
+}
+
+int lpr_for_stride(uint32_t stride) {
+    uint32_t segs = (stride + 15) / 16;
+    if (segs > 32) segs = 32;
+    int lpr = 1;
+    while ((uint32_t)lpr < segs) lpr <<= 1;
+    return lpr;
+}
+
+template <int LPR>
+void launch_fused(const GatherArgs& a, cudaStream_t st) {
+    constexpr int G = 32 / LPR;
+    uint64_t groups = (uint64_t)a.n_class_idx * a.n_q;
+    uint64_t warps = (groups + G - 1) / G;
+    unsigned blocks = (unsigned)((warps + 7) / 8);
+    if (blocks) gather_count_fused_kernel<LPR><<<blocks, 256, 0, st>>>(a);
+}
+
+template <int LPR>
+void launch_accum(const DevIndex* ixp, const SlowItem* items, uint32_t n_items, uint32_t n_chunks,
+                  const uint64_t* koffs, const uint64_t* hashes, uint64_t total_kmers,
+                  uint32_t* scores, cudaStream_t st) {
+    constexpr int G = 32 / LPR;
+    uint64_t groups = (uint64_t)n_items * n_chunks;
+    uint64_t warps = (groups + G - 1) / G;
+    unsigned blocks = (unsigned)((warps + 7) / 8);
+    if (blocks)
+        accum_scores_kernel<LPR><<<blocks, 256, 0, st>>>(ixp, items, n_items, n_chunks, koffs, hashes,
+                                                        total_kmers, scores);
+}
+
+void dispatch_accum(int lpr, const DevIndex* ixp, const SlowItem* items, uint32_t n_items,
+                    uint32_t n_chunks, const uint64_t* koffs, const uint64_t* hashes,
+                    uint64_t total_kmers, uint32_t* scores, cudaStream_t st) {
+    switch (lpr) {
+        case 1: launch_accum<1>(ixp, items, n_items, n_chunks, koffs, hashes, total_kmers, scores, st); break;
+        case 2: launch_accum<2>(ixp, items, n_items, n_chunks, koffs, hashes, total_kmers, scores, st); break;
+        case 4: launch_accum<4>(ixp, items, n_items, n_chunks, koffs, hashes, total_kmers, scores, st); break;
+        case 8: launch_accum<8>(ixp, items, n_items, n_chunks, koffs, hashes, total_kmers, scores, st); break;
+        case 16: launch_accum<16>(ixp, items, n_items, n_chunks, koffs, hashes, total_kmers, scores, st); break;
+        default: launch_accum<32>(ixp, items, n_items, n_chunks, koffs, hashes, total_kmers, scores, st); break;
+    }
+}
+
+// chunk a query's k-mers into items of at most PHY_FUSED_KMAX rows
+void push_items(std::vector<SlowItem>& items, uint32_t slot, uint32_t q, uint32_t K) {
+    for (uint32_t k0 = 0; k0 < K; k0 += PHY_FUSED_KMAX) {
+        SlowItem it;
+        it.slot = slot; it.query = q; it.k0 = k0;
+        it.k1 = K - k0 > PHY_FUSED_KMAX ? k0 + PHY_FUSED_KMAX : K;
+        items.push_back(it);
+    }
+}
+
+}  // namespace
+
+int phy_lpr_for_stride(uint32_t stride) { return lpr_for_stride(stride); }
+
+// Run the general path for `slots` (query ids) against index ix; scores into d_scores.
+static int run_general(phy_ctx* ctx, const HostIndex& ix, int ipos, const std::vector<uint32_t>& slot_queries,
+                       uint32_t* d_scores_out) {
+    std::vector<SlowItem> items;
+    for (uint32_t s = 0; s < slot_queries.size(); s++) push_items(items, s, slot_queries[s], ctx->h_nk[slot_queries[s]]);
+    const size_t n_sc = slot_queries.size() * (size_t)ix.d.n_docs;
+    PHY_CUDA(ctx, cudaMemsetAsync(d_scores_out, 0, n_sc * sizeof(uint32_t), ctx->stream));
+    if (items.empty()) return PHY_OK;
+    PHY_TRY(phy_ensure(ctx, ctx->d_items, items.size()));
+    PHY_TRY(phy_h2d(ctx, ctx->d_items.p, items.data(), items.size() * sizeof(SlowItem)));
+    const uint32_t n_chunks = (ix.d.stride + PHY_CHUNK_BYTES - 1) / PHY_CHUNK_BYTES;
+    dispatch_accum(ix.lpr, ctx->d_indexes.p + ipos, ctx->d_items.p, (uint32_t)items.size(), n_chunks,
+                   ctx->d_koffs.p, ctx->d_hashes.p, ctx->total_kmers, d_scores_out, ctx->stream);
+    ctx->launches++;
+    PHY_CUDA(ctx, cudaGetLastError());
+    return PHY_OK;
+}
+
+int phy_launch_scores(phy_ctx* ctx, int idx_id, uint32_t* d_out_scores) {
+    const HostIndex& ix = ctx->idx[idx_id];
+    std::vector<uint32_t> qs;
+    for (uint32_t q = 0; q < ctx->nq; q++) qs.push_back(q);
+    return run_general(ctx, ix, idx_id, qs, d_out_scores);
+}
+
+int phy_launch_gather(phy_ctx* ctx, const phy_match_params* p) {
+    // per-query minimum score T (host double arithmetic, identical to the oracle / cobs)
+    std::vector<uint32_t> T(ctx->nq), fastq, slowq;
+    for (uint32_t q = 0; q < ctx->nq; q++) {
+        double x = p->threshold * (double)ctx->h_nk[q];
+        double r = p->floor_mode ? floor(x) : ceil(x);
+        T[q] = r < 0 ? 0u : (r > 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)r);
+        if (ctx->h_nk[q] == 0) continue;
+        (ctx->h_nk[q] <= PHY_FUSED_KMAX ? fastq : slowq).push_back(q);
+    }
+    // longest first: balances the tail and keeps co-resident groups of a warp similar
+    std::stable_sort(fastq.begin(), fastq.end(), [&](uint32_t a, uint32_t b) { return ctx->h_nk[a] > ctx->h_nk[b]; });
+    PHY_TRY(phy_ensure(ctx, ctx->d_T, ctx->nq + 1));
+    PHY_TRY(phy_h2d(ctx, ctx->d_T.p, T.data(), T.size() * sizeof(uint32_t)));
+    PHY_TRY(phy_ensure(ctx, ctx->d_qlist, ctx->nq + 1));
+    if (!fastq.empty()) PHY_TRY(phy_h2d(ctx, ctx->d_qlist.p, fastq.data(), fastq.size() * sizeof(uint32_t)));
+    PHY_TRY(phy_ensure(ctx, ctx->d_qcount, ctx->nq + 1));
+    PHY_TRY(phy_ensure(ctx, ctx->d_counters, 8));
+
+    // index classes
+    std::vector<uint32_t> cls[6], wide;  // lpr 1,2,4,8,16,32 ; wide = stride > 512 (general path)
+    for (size_t i = 0; i < ctx->idx.size(); i++) {
+        const HostIndex& ix = ctx->idx[i];
+        if (!ix.alive || !ix.committed) continue;
+        if (ix.d.stride > PHY_CHUNK_BYTES) { wide.push_back((uint32_t)i); continue; }
+        int c = 0;
+        while ((1 << c) < ix.lpr) c++;
+        cls[c].push_back((uint32_t)i);
+    }
+    std::vector<uint32_t> class_flat;
+    size_t class_off[6];
+    for (int c = 0; c < 6; c++) { class_off[c] = class_flat.size(); class_flat.insert(class_flat.end(), cls[c].begin(), cls[c].end()); }
+    uint32_t* d_class = nullptr;
+    if (!class_flat.empty()) {
+        PHY_TRY(phy_ensure(ctx, ctx->d_class, class_flat.size()));
+        d_class = ctx->d_class.p;
+        PHY_TRY(phy_h2d(ctx, d_class, class_flat.data(), class_flat.size() * sizeof(uint32_t)));
+    }
+
+    uint64_t units_cap = ctx->d_units.cap, hits_cap = ctx->d_hits.cap;
+    if (units_cap < 4096) units_cap = 1 << 16;
+    if (hits_cap < 4096) hits_cap = 1 << 20;
+    for (int attempt = 0; attempt < 3; attempt++) {
+        PHY_TRY(phy_ensure(ctx, ctx->d_units, units_cap));
+        PHY_TRY(phy_ensure(ctx, ctx->d_hits, hits_cap));
+        PHY_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, 2 * sizeof(unsigned long long), ctx->stream));
+        PHY_CUDA(ctx, cudaMemsetAsync(ctx->d_qcount.p, 0, (ctx->nq + 1) * sizeof(uint32_t), ctx->stream));
+        GatherArgs a;
+        a.indexes = ctx->d_indexes.p;
+        a.qlist = ctx->d_qlist.p; a.n_q = (uint32_t)fastq.size();
+        a.koffs = ctx->d_koffs.p; a.nk = ctx->d_nk.p; a.T = ctx->d_T.p;
+        a.hashes = ctx->d_hashes.p; a.total_kmers = ctx->total_kmers;
+        a.top_n = p->top_n;
+        a.units = ctx->d_units.p; a.units_cap = ctx->d_units.cap;
+        a.hits = ctx->d_hits.p; a.hits_cap = ctx->d_hits.cap;
+        a.counters = ctx->d_counters.p; a.qcount = ctx->d_qcount.p;
+        if (!fastq.empty()) {
+            for (int c = 0; c < 6; c++) {
+                if (cls[c].empty()) continue;
+                a.class_idx = d_class + class_off[c];
+                a.n_class_idx = (uint32_t)cls[c].size();
+                switch (c) {
+                    case 0: launch_fused<1>(a, ctx->stream); break;
+                    case 1: launch_fused<2>(a, ctx->stream); break;
+                    case 2: launch_fused<4>(a, ctx->stream); break;
+                    case 3: launch_fused<8>(a, ctx->stream); break;
+                    case 4: launch_fused<16>(a, ctx->stream); break;
+                    default: launch_fused<32>(a, ctx->stream); break;
+                }
+                ctx->launches++;
+                PHY_CUDA(ctx, cudaGetLastError());
+            }
+        }
+        // general path: long queries against every index; every query against wide indexes
+        for (size_t i = 0; i < ctx->idx.size(); i++) {
+            const HostIndex& ix = ctx->idx[i];
+            if (!ix.alive || !ix.committed) continue;
+            const bool is_wide = ix.d.stride > PHY_CHUNK_BYTES;
+            std::vector<uint32_t> qs = slowq;
+            if (is_wide) qs.insert(qs.end(), fastq.begin(), fastq.end());
+            if (qs.empty()) continue;
+            // bounded scratch: process slots in groups of <= 256 MB of scores
+            size_t per = std::max<size_t>(1, (size_t)(64u << 20) / std::max<uint32_t>(1, ix.d.n_docs));
+            for (size_t s0 = 0; s0 < qs.size(); s0 += per) {
+                std::vector<uint32_t> part(qs.begin() + s0, qs.begin() + std::min(qs.size(), s0 + per));
+                PHY_TRY(phy_ensure(ctx, ctx->d_scores, part.size() * (size_t)ix.d.n_docs));
+                PHY_TRY(phy_ensure(ctx, ctx->d_slotq, part.size()));
+                PHY_TRY(phy_h2d(ctx, ctx->d_slotq.p, part.data(), part.size() * sizeof(uint32_t)));
+                PHY_TRY(run_general(ctx, ix, (int)i, part, ctx->d_scores.p));
+                select_scores_kernel<<<(unsigned)part.size(), 256, 0, ctx->stream>>>(
+                    ctx->d_scores.p, ix.d.n_docs, ctx->d_slotq.p, ctx->d_T.p, ctx->d_nk.p, p->top_n,
+                    ix.d.idx_id, ctx->d_units.p, ctx->d_units.cap, ctx->d_hits.p, ctx->d_hits.cap,
+                    ctx->d_counters.p, ctx->d_qcount.p);
+                ctx->launches++;
+                PHY_CUDA(ctx, cudaGetLastError());
+            }
+        }
+        unsigned long long cnt[2];
+        PHY_CUDA(ctx, cudaMemcpyAsync(cnt, ctx->d_counters.p, sizeof cnt, cudaMemcpyDeviceToHost, ctx->stream));
+        PHY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (cnt[0] <= ctx->d_hits.cap && cnt[1] <= ctx->d_units.cap) {
+            ctx->n_hits = cnt[0];
+            ctx->n_units = cnt[1];
+            return PHY_OK;
+        }
+        hits_cap = std::max<uint64_t>(cnt[0], hits_cap);
+        units_cap = std::max<uint64_t>(cnt[1], units_cap);
+    }
+    phy_set_error(ctx, "result buffers could not be sized");
+    return PHY_ERR_NOMEM;
+}

@@ -1,0 +1,149 @@
+// kmer_hash.cu -- K1: canonical k-mers of the queries and their XXH64 values.
+//
+// Replaces cobs `canonicalize_kmer` + `create_hashes` (SURVEY.md 8(a) a4, Appendix
+// A.3/A.4; called from /root/reference/scripts/run_cobs_streaming.sh:24-29):
+//   hash[j][g] = XXH64(canonical ASCII k-mer g, k, seed=j)
+// The hash is index independent; `% signature_size` happens in the gather kernel.
+// One thread per query k-mer; integer only; ~0.3% of the step time.
+#include "phy_internal.cuh"
+
+namespace {
+
+constexpr uint64_t XP1 = 0x9E3779B185EBCA87ULL;
+constexpr uint64_t XP2 = 0xC2B2AE3D27D4EB4FULL;
+constexpr uint64_t XP3 = 0x165667B19E3779F9ULL;
+constexpr uint64_t XP4 = 0x85EBCA77C2B2AE63ULL;
+constexpr uint64_t XP5 = 0x27D4EB2F165667C5ULL;
+
+__device__ __forceinline__ uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+__device__ __forceinline__ uint64_t xround(uint64_t acc, uint64_t in) {
+    return rotl64(acc + in * XP2, 31) * XP1;
+}
+
+// XXH64 of the k (<32) bytes packed little-endian in w[0..3] (short-input path of the spec).
+__device__ __forceinline__ uint64_t xxh64_packed(const uint64_t (&w)[4], const int k, uint64_t seed) {
+    uint64_t h = seed + XP5 + (uint64_t)k;
+    const int n8 = k >> 3;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        if (i < n8) {
+            h ^= xround(0, w[i]);
+            h = rotl64(h, 27) * XP1 + XP4;
+        }
+    }
+    // remaining k & 7 bytes live in w[n8]
+    uint64_t tail = n8 == 0 ? w[0] : (n8 == 1 ? w[1] : (n8 == 2 ? w[2] : w[3]));
+    int rem = k & 7;
+    if (rem >= 4) {
+        h ^= (tail & 0xFFFFFFFFULL) * XP1;
+        h = rotl64(h, 23) * XP2 + XP3;
+        tail >>= 32;
+        rem -= 4;
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        if (i < rem) {
+            h ^= (tail & 0xFFULL) * XP5;
+            h = rotl64(h, 11) * XP1;
+            tail >>= 8;
+        }
+    }
+    h ^= h >> 33;
+    h *= XP2;
+    h ^= h >> 29;
+    h *= XP3;
+    h ^= h >> 32;
+    return h;
+}
+
+// error word layout: bit 63 = an invalid letter was seen, low 32 bits = smallest query id
+__device__ __forceinline__ void report_bad(unsigned long long* err, uint32_t q) {
+    atomicMin(err, 0x8000000000000000ULL | (unsigned long long)q);
+}
+
+template <int KT>  // KT = 31 (fast path) or 0 (runtime k <= 31)
+__global__ void __launch_bounds__(256) kmer_hash_kernel(
+    const char* __restrict__ seq, const uint64_t* __restrict__ qoffs,
+    const uint64_t* __restrict__ koffs, uint32_t nq, uint64_t total_kmers, int k_rt,
+    int canonicalize, uint32_t num_hashes, uint64_t* __restrict__ hashes,
+    unsigned long long* __restrict__ err) {
+    const int k = KT ? KT : k_rt;
+    uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total_kmers) return;
+    // query of k-mer g: last q with koffs[q] <= g
+    uint32_t lo = 0, hi = nq;  // invariant: koffs[lo] <= g < koffs[hi]
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(&koffs[mid]) <= g) lo = mid; else hi = mid;
+    }
+    const uint32_t q = lo;
+    const char* s = seq + __ldg(&qoffs[q]) + (g - __ldg(&koffs[q]));
+
+    uint64_t fwd = 0, rc = 0;
+    bool bad = false;
+#pragma unroll
+    for (int i = 0; i < 31; i++) {
+        if (i < k) {
+            uint32_t c = (uint8_t)__ldg(&s[i]);
+            uint32_t x = (c >> 1) & 3u;
+            uint32_t code = x ^ (x >> 1);  // A0 C1 G2 T3
+            bad |= ((0x54474341u >> (8 * code)) & 0xFFu) != c;
+            fwd = (fwd << 2) | code;
+            rc |= (uint64_t)(3u - code) << (2 * i);
+        }
+    }
+    if (bad) {
+        report_bad(err, q);
+        return;
+    }
+    // ASCII order A<C<G<T equals the order of the MSB-first 2-bit packing
+    uint64_t v = (canonicalize && rc < fwd) ? rc : fwd;
+    uint64_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 31; i++) {
+        if (i < k) {
+            uint32_t code = (uint32_t)(v >> (2 * (k - 1 - i))) & 3u;
+            uint64_t ch = (0x54474341u >> (8 * code)) & 0xFFu;
+            w[i >> 3] |= ch << (8 * (i & 7));
+        }
+    }
+    for (uint32_t j = 0; j < num_hashes; j++) hashes[(uint64_t)j * total_kmers + g] = xxh64_packed(w, k, j);
+}
+
+}  // namespace
+
+int phy_launch_hash(phy_ctx* ctx) {
+    if (ctx->total_kmers == 0) {
+        ctx->hashes_valid = true;
+        return PHY_OK;
+    }
+    const uint32_t nh = ctx->q_num_hashes;
+    PHY_TRY(phy_ensure(ctx, ctx->d_hashes, ctx->total_kmers * nh));
+    PHY_TRY(phy_ensure(ctx, ctx->d_counters, 8));
+    PHY_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p + 2, 0xFF, sizeof(unsigned long long), ctx->stream));
+    const uint64_t nblk = (ctx->total_kmers + 255) / 256;
+    if (nblk > 0x7FFFFFFFull) {
+        phy_set_error(ctx, "too many k-mers in one query block");
+        return PHY_ERR_ARG;
+    }
+    if (ctx->q_term_size == 31) {
+        kmer_hash_kernel<31><<<(unsigned)nblk, 256, 0, ctx->stream>>>(
+            ctx->d_seq.p, ctx->d_qoffs.p, ctx->d_koffs.p, ctx->nq, ctx->total_kmers, 31,
+            (int)ctx->q_canon, nh, ctx->d_hashes.p, ctx->d_counters.p + 2);
+    } else {
+        kmer_hash_kernel<0><<<(unsigned)nblk, 256, 0, ctx->stream>>>(
+            ctx->d_seq.p, ctx->d_qoffs.p, ctx->d_koffs.p, ctx->nq, ctx->total_kmers,
+            (int)ctx->q_term_size, (int)ctx->q_canon, nh, ctx->d_hashes.p, ctx->d_counters.p + 2);
+    }
+    ctx->launches++;
+    PHY_CUDA(ctx, cudaGetLastError());
+    unsigned long long e = 0;
+    PHY_CUDA(ctx, cudaMemcpyAsync(&e, ctx->d_counters.p + 2, sizeof e, cudaMemcpyDeviceToHost, ctx->stream));
+    PHY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (e != ~0ULL) {
+        phy_set_error(ctx, "query #%u holds a letter outside ACGT", (unsigned)(e & 0xFFFFFFFFu));
+        return PHY_ERR_QUERY;
+    }
+    ctx->hashes_valid = true;
+    return PHY_OK;
+}

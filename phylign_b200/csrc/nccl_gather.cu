@@ -1,0 +1,191 @@
+// nccl_gather.cu -- multi-GPU exchange of the match stage.
+//
+// Batches (indexes) are independent, so the gather/count path has no collective at all:
+// each GPU holds a shard of the indexes and sees every query.  The only real exchange is
+// the one filter_queries.py performs across batch files
+// (/root/reference/scripts/filter_queries.py:178-185): the per-GPU top-N + ties lists are
+// gathered over NVLink to rank 0 and merged once more with the same kernel.  Correct
+// because global top-N + ties is a subset of the union of per-GPU top-N + ties.
+//
+// libnccl is resolved with dlopen at phy_nccl_init time, so single-GPU users never need it
+// and the process shares whichever libnccl.so.2 is already loaded (e.g. PyTorch's).
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+
+#include "phy_internal.cuh"
+
+namespace {
+
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+
+int load_nccl(phy_ctx* ctx) {
+    if (g_nccl.handle) return PHY_OK;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    void* h = nullptr;
+    for (const char* n : names) {
+        h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) {
+        phy_set_error(ctx, "cannot load libnccl.so.2: %s", dlerror());
+        return PHY_ERR_NCCL;
+    }
+#define LOAD(field, sym)                                         \
+    g_nccl.field = (decltype(g_nccl.field))dlsym(h, sym);        \
+    if (!g_nccl.field) {                                         \
+        phy_set_error(ctx, "libnccl lacks symbol %s", sym);      \
+        return PHY_ERR_NCCL;                                     \
+    }
+    LOAD(GetUniqueId, "ncclGetUniqueId")
+    LOAD(CommInitRank, "ncclCommInitRank")
+    LOAD(CommDestroy, "ncclCommDestroy")
+    LOAD(AllGather, "ncclAllGather")
+    LOAD(Send, "ncclSend")
+    LOAD(Recv, "ncclRecv")
+    LOAD(GroupStart, "ncclGroupStart")
+    LOAD(GroupEnd, "ncclGroupEnd")
+    LOAD(GetErrorString, "ncclGetErrorString")
+#undef LOAD
+    g_nccl.handle = h;
+    return PHY_OK;
+}
+
+#define PHY_NCCL(ctx, call)                                                                   \
+    do {                                                                                      \
+        ncclResult_t r_ = (call);                                                             \
+        if (r_ != ncclSuccess) {                                                              \
+            phy_set_error(ctx, "%s failed: %s", #call, g_nccl.GetErrorString(r_));            \
+            return PHY_ERR_NCCL;                                                              \
+        }                                                                                     \
+    } while (0)
+
+// per-query candidate count over all ranks; foffs_all = [R][nq+1]
+__global__ void __launch_bounds__(256) rank_totals_kernel(const uint64_t* __restrict__ foffs_all, uint32_t n_ranks,
+                                                          uint32_t nq, uint32_t* __restrict__ totals) {
+    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    uint64_t t = 0;
+    for (uint32_t r = 0; r < n_ranks; r++) {
+        const uint64_t* f = foffs_all + (uint64_t)r * (nq + 1);
+        t += f[q + 1] - f[q];
+    }
+    totals[q] = (uint32_t)t;
+}
+
+// copy every rank's candidates of query q behind each other into the merge segments
+__global__ void __launch_bounds__(128) regroup_kernel(const uint64_t* __restrict__ foffs_all,
+                                                      const uint64_t* __restrict__ rank_base, uint32_t n_ranks,
+                                                      uint32_t nq, const phy_cand* __restrict__ recv,
+                                                      const uint64_t* __restrict__ qoffs_c,
+                                                      uint64_t* __restrict__ ckey, uint32_t* __restrict__ cval) {
+    for (uint32_t q = blockIdx.x; q < nq; q += gridDim.x) {
+        uint64_t dst = qoffs_c[q];
+        for (uint32_t r = 0; r < n_ranks; r++) {
+            const uint64_t* f = foffs_all + (uint64_t)r * (nq + 1);
+            const uint64_t src = rank_base[r] + f[q];
+            const uint32_t n = (uint32_t)(f[q + 1] - f[q]);
+            for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+                phy_cand c = recv[src + i];
+                ckey[dst + i] = ((uint64_t)(~c.score) << 32) | ((uint64_t)c.batch_rank << 20) | c.ref_rank;
+                cval[dst + i] = c.doc;
+            }
+            dst += n;
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int phy_nccl_unique_id(void* id_out) {
+    if (!id_out) return PHY_ERR_ARG;
+    PHY_TRY(load_nccl(nullptr));
+    static_assert(sizeof(ncclUniqueId) == PHY_NCCL_ID_BYTES, "ncclUniqueId size");
+    ncclUniqueId id;
+    PHY_NCCL(nullptr, g_nccl.GetUniqueId(&id));
+    memcpy(id_out, &id, sizeof id);
+    return PHY_OK;
+}
+
+extern "C" int phy_nccl_init(phy_ctx* ctx, const void* id, int rank, int n_ranks) {
+    if (!ctx || !id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return PHY_ERR_ARG;
+    PHY_TRY(load_nccl(ctx));
+    PHY_CUDA(ctx, cudaSetDevice(ctx->device));
+    ncclUniqueId uid;
+    memcpy(&uid, id, sizeof uid);
+    ncclComm_t comm;
+    PHY_NCCL(ctx, g_nccl.CommInitRank(&comm, n_ranks, uid, rank));
+    ctx->nccl_comm = comm;
+    ctx->rank = rank;
+    ctx->n_ranks = n_ranks;
+    return PHY_OK;
+}
+
+// After the local merge: gather every rank's (d_foffs, d_final) on rank 0 and merge again.
+int phy_nccl_merge(phy_ctx* ctx, uint32_t top_n) {
+    ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
+    const uint32_t nq = ctx->nq, R = (uint32_t)ctx->n_ranks;
+    // (1) every rank learns every rank's per-query offsets (tiny: R x (nq+1) x 8 B)
+    DevBuf<uint64_t>& all = ctx->d_foffs_all;
+    PHY_TRY(phy_ensure(ctx, all, (size_t)R * (nq + 1)));
+    PHY_NCCL(ctx, g_nccl.AllGather(ctx->d_foffs.p, all.p, nq + 1, ncclUint64, comm, ctx->stream));
+    std::vector<uint64_t> totals(R), base(R + 1, 0);
+    for (uint32_t r = 0; r < R; r++)
+        PHY_CUDA(ctx, cudaMemcpyAsync(&totals[r], all.p + (size_t)r * (nq + 1) + nq, sizeof(uint64_t),
+                                      cudaMemcpyDeviceToHost, ctx->stream));
+    PHY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (uint32_t r = 0; r < R; r++) base[r + 1] = base[r] + totals[r];
+    // (2) candidate lists -> rank 0 over NVLink
+    static_assert(sizeof(phy_cand) == 16, "phy_cand is sent as 4 x uint32");
+    if (ctx->rank == 0) {
+        PHY_TRY(phy_ensure(ctx, ctx->d_recv, base[R] + 1));
+        if (totals[0])
+            PHY_CUDA(ctx, cudaMemcpyAsync(ctx->d_recv.p, ctx->d_final.p, totals[0] * sizeof(phy_cand),
+                                          cudaMemcpyDeviceToDevice, ctx->stream));
+        PHY_NCCL(ctx, g_nccl.GroupStart());
+        for (uint32_t r = 1; r < R; r++)
+            if (totals[r])
+                PHY_NCCL(ctx, g_nccl.Recv(ctx->d_recv.p + base[r], totals[r] * 4, ncclUint32, (int)r, comm, ctx->stream));
+        PHY_NCCL(ctx, g_nccl.GroupEnd());
+    } else {
+        if (totals[ctx->rank])
+            PHY_NCCL(ctx, g_nccl.Send(ctx->d_final.p, totals[ctx->rank] * 4, ncclUint32, 0, comm, ctx->stream));
+        ctx->n_final = 0;
+        PHY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return PHY_OK;
+    }
+    // (3) rank 0: regroup by query and run the same sort + cut kernel over the union
+    PHY_TRY(phy_ensure(ctx, ctx->d_rank_base, R + 1));
+    PHY_TRY(phy_h2d(ctx, ctx->d_rank_base.p, base.data(), (R + 1) * sizeof(uint64_t)));
+    PHY_TRY(phy_ensure(ctx, ctx->d_qcount, nq + 1));
+    if (nq) {
+        rank_totals_kernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(all.p, R, nq, ctx->d_qcount.p);
+        ctx->launches++;
+    }
+    uint64_t total = 0;
+    PHY_TRY(phy_ensure(ctx, ctx->d_qoffs_c, nq + 2));
+    PHY_TRY(phy_exscan(ctx, ctx->d_qcount.p, nq, ctx->d_qoffs_c.p, &total));
+    PHY_TRY(phy_ensure(ctx, ctx->d_ckey, total + 1));
+    PHY_TRY(phy_ensure(ctx, ctx->d_cval, total + 1));
+    if (nq && total) {
+        unsigned blocks = (unsigned)std::min<uint64_t>(nq, 148ull * 32);
+        regroup_kernel<<<blocks, 128, 0, ctx->stream>>>(all.p, ctx->d_rank_base.p, R, nq, ctx->d_recv.p,
+                                                       ctx->d_qoffs_c.p, ctx->d_ckey.p, ctx->d_cval.p);
+        ctx->launches++;
+        PHY_CUDA(ctx, cudaGetLastError());
+    }
+    return phy_merge_segments(ctx, top_n);
+}

@@ -1,0 +1,267 @@
+"""Host-side driver of the match stage: the Python mirror of what the reference does with
+`cobs query | postprocess_cobs.py` per batch and `filter_queries.py` over all batches
+(/root/reference/Snakefile:390-520), on top of the C ABI of libphylign_cuda.so.
+
+Python keeps what SURVEY.md 8(b) leaves to the host: header parsing, document names,
+rank tables for the merge key, text formatting.  All arithmetic runs in the CUDA library;
+nothing here falls back to a CPU implementation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib
+from .cobs_index import IndexStream, parse_bytes, ref_of
+
+UNIT_DT = np.dtype([("query", "<u4"), ("index", "<u4"), ("n_pass", "<u4"), ("n_kept", "<u4"),
+                    ("offset", "<u8")])
+HIT_DT = np.dtype([("doc", "<u4"), ("score", "<u4")])
+CAND_DT = np.dtype([("score", "<u4"), ("batch_rank", "<u4"), ("doc", "<u4"), ("ref_rank", "<u4")])
+
+
+class ResidentIndex:
+    def __init__(self, idx_id, batch, header):
+        self.idx_id = idx_id
+        self.batch = batch
+        self.header = header
+        self.doc_names = header.doc_names
+        self.batch_rank = idx_id
+
+
+class MatchResult:
+    """Non-empty (query, index) blocks of one match call (numpy copies of phy_results)."""
+
+    def __init__(self, units, hits, n_kmers, n_queries, h2d_bytes, d2h_bytes):
+        self.units, self.hits, self.n_kmers = units, hits, n_kmers
+        self.n_queries = n_queries
+        self.h2d_bytes, self.d2h_bytes = h2d_bytes, d2h_bytes
+
+    def units_of(self, idx_id):
+        lo = np.searchsorted(self.units["index"], idx_id, "left")
+        hi = np.searchsorted(self.units["index"], idx_id, "right")
+        return self.units[lo:hi]
+
+    def hits_of(self, unit):
+        o = int(unit["offset"])
+        return self.hits[o:o + int(unit["n_kept"])]
+
+
+class Matcher:
+    def __init__(self, device: int = 0, hbm_budget: int = 0):
+        self._L = _lib.load()
+        self._ctx = C.c_void_p()
+        _lib.check(self._L.phy_ctx_create(C.byref(self._ctx), device, hbm_budget))
+        self.device = device
+        self.indexes: dict[int, ResidentIndex] = {}
+        self.records: list = []
+        self._seq_keepalive = None
+
+    # ------------------------------------------------------------------ lifecycle
+    def close(self):
+        if self._ctx:
+            self._L.phy_ctx_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, code):
+        _lib.check(code, self._ctx)
+
+    # ------------------------------------------------------------------ index store
+    def _begin(self, batch, hdr):
+        idx = C.c_int(-1)
+        self._ck(self._L.phy_index_begin(self._ctx, batch.encode(), hdr.term_size, hdr.canonicalize,
+                                         hdr.signature_size, hdr.num_hashes, hdr.n_docs, C.byref(idx)))
+        return idx.value
+
+    def _push(self, idx_id, chunk):
+        n = len(chunk)
+        if n == 0:
+            return
+        if isinstance(chunk, (bytes, bytearray)):
+            buf = (C.c_char * n).from_buffer_copy(chunk) if isinstance(chunk, bytes) else \
+                (C.c_char * n).from_buffer(chunk)
+        else:
+            buf = (C.c_char * n).from_buffer(chunk)
+        self._ck(self._L.phy_index_push(self._ctx, idx_id, buf, n))
+
+    def load_index(self, path, batch: str | None = None) -> int:
+        """Stream a `.cobs_classic[.xz]` file (or pipe) into HBM; returns the index id."""
+        if batch is None:
+            batch = os.path.basename(str(path)).split(".cobs_classic")[0]
+        with IndexStream(path) as st:
+            idx_id = self._begin(batch, st.header)
+            try:
+                for chunk in st.body_chunks():
+                    self._push(idx_id, chunk)
+                self._ck(self._L.phy_index_commit(self._ctx, idx_id))
+            except Exception:
+                self._L.phy_index_evict(self._ctx, idx_id)
+                raise
+        self.indexes[idx_id] = ResidentIndex(idx_id, batch, st.header)
+        return idx_id
+
+    def load_index_bytes(self, raw: bytes, batch: str) -> int:
+        hdr, body = parse_bytes(raw)
+        idx_id = self._begin(batch, hdr)
+        try:
+            self._push(idx_id, body)
+            self._ck(self._L.phy_index_commit(self._ctx, idx_id))
+        except Exception:
+            self._L.phy_index_evict(self._ctx, idx_id)
+            raise
+        self.indexes[idx_id] = ResidentIndex(idx_id, batch, hdr)
+        return idx_id
+
+    def add_synth_index(self, batch, spec: _lib.SynthSpec, signature_size, doc_names=None,
+                        num_hashes=1, canonicalize=1):
+        """Bench/test utility: build an index on the device from procedural genomes."""
+        from .cobs_index import ClassicHeader
+        names = doc_names or [f"r{d:06d}_SYN{d:06d}" for d in range(spec.n_docs)]
+        hdr = ClassicHeader(31, canonicalize, spec.n_docs, signature_size, num_hashes, names)
+        idx_id = self._begin(batch, hdr)
+        self._ck(self._L.phy_index_synth(self._ctx, idx_id, C.byref(spec)))
+        self.indexes[idx_id] = ResidentIndex(idx_id, batch, hdr)
+        return idx_id
+
+    def evict(self, idx_id):
+        self._ck(self._L.phy_index_evict(self._ctx, idx_id))
+        self.indexes.pop(idx_id, None)
+
+    def index_info(self, idx_id) -> _lib.IndexInfo:
+        info = _lib.IndexInfo()
+        self._ck(self._L.phy_index_info_get(self._ctx, idx_id, C.byref(info)))
+        return info
+
+    def download_index(self, idx_id) -> bytes:
+        n = self.indexes[idx_id].header.body_size
+        buf = C.create_string_buffer(n)
+        self._ck(self._L.phy_index_download(self._ctx, idx_id, buf, n))
+        return buf.raw
+
+    def set_ranks(self, all_batches=None):
+        """Upload the integer ranks behind the merge key (-kmers, batch, ref) of
+        filter_queries.py:135.  `all_batches`: every batch name of the job (all GPUs)."""
+        names = sorted(set(all_batches) if all_batches is not None
+                       else {ix.batch for ix in self.indexes.values()})
+        rank_of = {b: i for i, b in enumerate(names)}
+        for ix in self.indexes.values():
+            refs = [ref_of(n) for n in ix.doc_names]
+            order = sorted(range(len(refs)), key=lambda d: refs[d])
+            rr = np.empty(len(refs), dtype=np.uint32)
+            rr[order] = np.arange(len(refs), dtype=np.uint32)
+            ix.batch_rank = rank_of[ix.batch]
+            self._ck(self._L.phy_index_set_ranks(self._ctx, ix.idx_id, ix.batch_rank, rr.ctypes.data))
+        self.batch_names = names
+        return names
+
+    # ------------------------------------------------------------------ queries
+    def set_queries(self, records):
+        """records = [(header, seq str|bytes)]; sequences must be upper-case ACGT."""
+        self.records = [(h, s if isinstance(s, bytes) else s.encode()) for h, s in records]
+        cat = b"".join(s for _, s in self.records)
+        offs = np.zeros(len(self.records) + 1, dtype=np.uint64)
+        if self.records:
+            offs[1:] = np.cumsum([len(s) for _, s in self.records], dtype=np.uint64)
+        self.set_queries_raw(cat, offs)
+
+    def set_queries_raw(self, cat: bytes, offs: np.ndarray):
+        offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        self._seq_keepalive = (cat, offs)
+        self._ck(self._L.phy_queries_set(self._ctx, cat, offs.ctypes.data, len(offs) - 1))
+
+    # ------------------------------------------------------------------ match
+    def match_run(self, threshold: float, top_n: int = 0, floor_mode: bool = False, merge_top_n: int = 0):
+        p = _lib.MatchParams(float(threshold), int(top_n), int(bool(floor_mode)))
+        self._ck(self._L.phy_match_run(self._ctx, C.byref(p), int(merge_top_n)))
+
+    def fetch(self) -> MatchResult:
+        rp = C.POINTER(_lib.Results)()
+        self._ck(self._L.phy_results_fetch(self._ctx, C.byref(rp)))
+        try:
+            r = rp.contents
+            nu, nh, nq = int(r.n_units), int(r.n_hits), int(r.n_queries)
+            units = np.frombuffer(C.string_at(r.units, nu * UNIT_DT.itemsize), dtype=UNIT_DT).copy() \
+                if nu else np.zeros(0, UNIT_DT)
+            hits = np.frombuffer(C.string_at(r.hits, nh * HIT_DT.itemsize), dtype=HIT_DT).copy() \
+                if nh else np.zeros(0, HIT_DT)
+            nk = np.frombuffer(C.string_at(r.n_kmers, nq * 4), dtype=np.uint32).copy() if nq else \
+                np.zeros(0, np.uint32)
+            return MatchResult(units, hits, nk, nq, int(r.h2d_bytes), int(r.d2h_bytes))
+        finally:
+            self._L.phy_results_free(rp)
+
+    def match(self, threshold: float, top_n: int = 0, floor_mode: bool = False, merge_top_n: int = 0):
+        self.match_run(threshold, top_n, floor_mode, merge_top_n)
+        return self.fetch()
+
+    def merged(self):
+        """(offs[nq+1], cands structured array) of the cross-index top-N + ties merge."""
+        mp = C.POINTER(_lib.Merged)()
+        self._ck(self._L.phy_merged_fetch(self._ctx, C.byref(mp)))
+        try:
+            m = mp.contents
+            nq = int(m.n_queries)
+            offs = np.frombuffer(C.string_at(m.offs, (nq + 1) * 8), dtype=np.uint64).copy()
+            n = int(offs[-1])
+            cands = np.frombuffer(C.string_at(m.cands, n * CAND_DT.itemsize), dtype=CAND_DT).copy() \
+                if n else np.zeros(0, CAND_DT)
+            return offs, cands
+        finally:
+            self._L.phy_merged_free(mp)
+
+    def scores(self, idx_id) -> np.ndarray:
+        nq = len(self._seq_keepalive[1]) - 1
+        d = self.indexes[idx_id].header.n_docs
+        out = np.zeros((nq, d), dtype=np.uint32)
+        self._ck(self._L.phy_scores(self._ctx, idx_id, out.ctypes.data))
+        return out
+
+    # ------------------------------------------------------------------ timing / bench hooks
+    def timer_start(self):
+        self._ck(self._L.phy_timer_start(self._ctx))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        self._ck(self._L.phy_timer_stop(self._ctx, C.byref(ms)))
+        return ms.value
+
+    def sync(self):
+        self._ck(self._L.phy_sync(self._ctx))
+
+    def flush_l2(self):
+        self._ck(self._L.phy_flush_l2(self._ctx))
+
+    def phase_ms(self):
+        a = (C.c_float * 4)()
+        self._ck(self._L.phy_last_phase_ms(self._ctx, a))
+        return list(a)
+
+    def synth_reads(self, specs, reads_seed, first_read, n_reads, read_len, random_q8=51, err_q16=655):
+        arr = (_lib.SynthSpec * len(specs))(*specs)
+        out = C.create_string_buffer(n_reads * read_len)
+        self._ck(self._L.phy_synth_reads(self._ctx, arr, len(specs), reads_seed, first_read, n_reads,
+                                         read_len, random_q8, err_q16, out))
+        return out.raw
+
+    def nccl_init(self, uid: bytes, rank: int, n_ranks: int):
+        self._ck(self._L.phy_nccl_init(self._ctx, uid, rank, n_ranks))
+
+
+def nccl_unique_id() -> bytes:
+    buf = C.create_string_buffer(_lib.NCCL_ID_BYTES)
+    _lib.check(_lib.load().phy_nccl_unique_id(buf))
+    return buf.raw

@@ -1,0 +1,113 @@
+"""CPU-only tests of the host side: C-ABI surface, index container, readers, text formats."""
+import gzip
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle
+from tests import helpers as H
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from phylign_b200 import _lib, build
+    build.build()
+    L = _lib.load()
+    header = open(os.path.join(ROOT, "include", "phylign_cuda.h")).read()
+    declared = set(re.findall(r"\b(phy_[a-z0-9_]+)\s*\(", header))
+    declared -= {"phy_ctx"}
+    assert declared, "no declarations found"
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} declared in include/phylign_cuda.h but not exported"
+        assert name in _lib.PROTOTYPES, f"{name} has no ctypes prototype"
+    assert L.phy_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_gpu():
+    """On a box without a GPU the product must fail loudly, never compute on the CPU."""
+    import ctypes as C
+    from phylign_b200 import _lib
+    L = _lib.load()
+    n = C.c_int(-1)
+    rc = L.phy_device_count(C.byref(n))
+    if rc == 0:
+        pytest.skip("a GPU is visible here")
+    assert rc == -1 and n.value == 0
+    from phylign_b200.matcher import Matcher
+    with pytest.raises(_lib.PhylignCudaError):
+        Matcher(0)
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "phylign_b200")):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, fn)).read()
+                assert not re.search(r"^\s*(import|from)\s+oracle", src, re.M), fn
+                assert "liboracle" not in src and "cobs_oracle.h" not in src, fn
+
+
+@pytest.mark.parametrize("batch", H.GOLDEN_BATCHES)
+def test_index_stream_parses_golden_xz(batch):
+    from phylign_b200.cobs_index import IndexStream, parse_bytes
+    raw = H.golden_index_bytes(batch)
+    oidx = oracle.OracleIndex.parse(raw)
+    with IndexStream(os.path.join(H.GOLDEN, f"{batch}.cobs_classic.xz"), chunk_bytes=10007) as st:
+        h = st.header
+        body = b"".join(bytes(c) for c in st.body_chunks())
+    assert (h.term_size, h.canonicalize, h.n_docs, h.signature_size, h.num_hashes) == \
+        (31, 1, oidx.n_docs, oidx.signature_size, 1)
+    assert h.doc_names == oidx.doc_names and h.header_size == oidx.header_size
+    assert body == oidx.body.tobytes()
+    h2, body2 = parse_bytes(raw)
+    assert body2 == body and h2.to_bytes() == raw[:h.header_size]
+
+
+def test_index_stream_rejects_bad_sizes(tmp_path):
+    from phylign_b200.cobs_index import IndexFormatError, IndexStream
+    raw = H.golden_index_bytes("bbb__01")
+    for name, data in (("short", raw[:-5]), ("long", raw + b"xx"), ("magic", b"XOBS" + raw[4:])):
+        p = tmp_path / f"{name}.cobs_classic"
+        p.write_bytes(data)
+        with pytest.raises(IndexFormatError):
+            with IndexStream(str(p)) as st:
+                for _ in st.body_chunks():
+                    pass
+
+
+def test_fasta_readers(tmp_path):
+    from phylign_b200.fasta import read_cobs_records, read_fastx
+    p = tmp_path / "q.fa"
+    p.write_text(">a desc here\nACGT\nAC\n\n;b\nGG\n>empty\n>c\nTT\n")
+    assert read_cobs_records(p) == [("a desc here", "ACGTAC"), ("b", "GG"), ("c", "TT")]
+    assert read_cobs_records(os.path.join(H.GOLDEN, "queries.fa")) == \
+        H.read_fasta(os.path.join(H.GOLDEN, "queries.fa"))
+    fq = tmp_path / "r.fq"
+    fq.write_text("@r1 x\nACGT\n+\nIIII\n@r2\nGG\nTT\n+r2\nII\nII\n")
+    assert read_fastx(fq) == [("r1", "ACGT"), ("r2", "GGTT")]
+    assert [n for n, _ in read_fastx(p)] == ["a", "empty", "c"]  # ';' is not a readfq header
+
+
+def test_text_formatters_with_synthetic_results():
+    from phylign_b200.cobs_text import format_cobs_text, format_filter_fasta
+    from phylign_b200.matcher import CAND_DT, HIT_DT, UNIT_DT, MatchResult, ResidentIndex
+    from phylign_b200.cobs_index import ClassicHeader
+    hdr = ClassicHeader(31, 1, 3, 10, 1, ["zz9_SAMEA3", "ab1_SAMEA1", "qq2_SAMEA2"])
+    ix = ResidentIndex(0, "bb__01", hdr)
+    units = np.array([(0, 0, 3, 2, 0), (2, 0, 1, 1, 2)], dtype=UNIT_DT)
+    hits = np.array([(0, 6), (1, 6), (2, 8)], dtype=HIT_DT)
+    res = MatchResult(units, hits, np.array([10, 10, 10, 0], np.uint32), 4, 0, 0)
+    recs = [("q1 c", "A" * 40), ("q2", "C" * 40), ("q3", "G" * 40), ("e", "")]
+    assert format_cobs_text(recs, res, ix) == \
+        "*q1 c\t3\nzz9_SAMEA3\t6\nab1_SAMEA1\t6\n*q2\t0\n*q3\t1\nqq2_SAMEA2\t8\n"
+    assert format_cobs_text(recs, res, ix, strip_prefix=True) == \
+        "*q1 c\t3\n_SAMEA3\t6\n_SAMEA1\t6\n*q2\t0\n*q3\t1\n_SAMEA2\t8\n"
+    # SURVEY.md Appendix C vector
+    cands = np.array([(6, 0, 0, 0), (6, 1, 1, 0), (6, 1, 0, 1), (8, 0, 1, 0), (8, 1, 2, 0)], dtype=CAND_DT)
+    offs = np.array([0, 3, 3, 5], dtype=np.uint64)
+    refs = {0: ["SAMEB3", "SAMEB5"], 1: ["SAMEA3", "SAMEA1", "SAMEA5"]}
+    got = format_filter_fasta([("q1", "AC"), ("q2", "GT"), ("q3", "TT")], offs, cands, refs)
+    assert got == ">q1 SAMEB3,SAMEA1,SAMEA3\nAC\n>q2 \nGT\n>q3 SAMEB5,SAMEA5\nTT\n"
