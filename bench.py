@@ -1,0 +1,353 @@
+#!/usr/bin/env python3
+"""bench.py -- COBS-match throughput of the B200 path (and of the CPU oracle beside it).
+
+Workload (BASELINE.json configs[2]): 100k synthetic 1 kbp reads vs 64 synthetic batch
+indexes (4000 docs x 1 Mbp genomes each, k=31, 1 hash, fpr 0.3 -> ~1.43 GB per index)
+resident in HBM, threshold 0.7, top-N 100 + ties, per-query merge over all indexes.
+A step = one pass of all reads over all indexes.  N GPUs: the 64 indexes are sharded
+round-robin over the ranks (strong scaling, fixed total work), queries replicated, per-GPU
+candidate lists gathered with NCCL and merged on rank 0 inside the step.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "COBS-match query bases/s over whole index"
+UNIT = "bases/s"
+THRESHOLD, TOP_N = 0.7, 100
+READS_SEED, RANDOM_Q8, ERR_Q16 = 3, 51, 655
+
+
+def workload(args):
+    w = dict(n_indexes=args.indexes, n_docs=args.docs, genome_len=args.genome_len,
+             n_reads=args.reads, read_len=args.read_len)
+    w["signature_size"] = int(math.ceil((w["genome_len"] - 30) * (-1.0 / math.log(1.0 - 0.3))))
+    w["row_size"] = (w["n_docs"] + 7) // 8
+    w["kmers_per_read"] = max(w["read_len"] - 30, 0)
+    w["bases"] = w["n_reads"] * w["read_len"]
+    # algorithmic bytes = sum_q K_q * sum_b h_b * ceil(D_b/8)
+    w["alg_bytes"] = w["n_reads"] * w["kmers_per_read"] * w["n_indexes"] * w["row_size"]
+    w["kmer_docs"] = w["n_reads"] * w["kmers_per_read"] * w["n_indexes"] * w["n_docs"]
+    return w
+
+
+def spec_kwargs(i, w):
+    return dict(seed=1000 + i, n_docs=w["n_docs"], genome_len=w["genome_len"], clade_size=32,
+                clade_sub_q16=328, doc_sub_q16=328)
+
+
+def batch_name(i):
+    return f"synth_species_{i:03d}__01"
+
+
+def config_dict(w, extra=None):
+    c = {"workload": f"{w['n_reads']} synthetic {w['read_len']} bp reads vs {w['n_indexes']} synthetic "
+                     f"COBS classic indexes ({w['n_docs']} docs x {w['genome_len']} bp, k=31, h=1, fpr=0.3) "
+                     f"resident in HBM, -t {THRESHOLD}, top-{TOP_N}+ties, cross-index merge "
+                     "(BASELINE.json configs[2])",
+         "n_reads": w["n_reads"], "read_len": w["read_len"], "n_indexes": w["n_indexes"],
+         "docs_per_index": w["n_docs"], "threshold": THRESHOLD, "top_n": TOP_N,
+         "algorithmic_bytes_per_step": w["alg_bytes"], "kmer_docs_per_step": w["kmer_docs"],
+         "l2_hygiene": "inputs (index shard) exceed the 126 MB L2; no flush needed"}
+    if extra:
+        c.update(extra)
+    return c
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+# ------------------------------------------------------------------------------- CPU arm
+def oracle_index_from_device(m, idx_id, w):
+    """Wrap a device-built synthetic index as an oracle index in host RAM (setup, untimed)."""
+    import oracle
+    oidx = oracle.OracleIndex.new(w["n_docs"], w["signature_size"])
+    body = m.download_index(idx_id)
+    oidx.body.reshape(-1)[:] = np.frombuffer(body, dtype=np.uint8)
+    return oidx
+
+
+def time_oracle(oidx, reads, threads):
+    """Seconds for one pass of `reads` over ONE index, best of the two thread layouts."""
+    out = {}
+    for mode, name in ((0, "cobs-shape: queries serial, 128-doc slices over threads"),
+                       (1, "queries over threads")):
+        t0 = time.perf_counter()
+        oidx.query_batch(reads, THRESHOLD, threads=threads, mode=mode)
+        out[name] = time.perf_counter() - t0
+    best = min(out, key=out.get)
+    return out[best], best, out
+
+
+def run_reference(args, w, rank, world):
+    if rank != 0:
+        return
+    import oracle
+    oracle.build()
+    cores = host_cores()
+    n_sample = min(w["n_reads"], args.cpu_sample_reads)
+    specs_kw = [spec_kwargs(i, w) for i in range(w["n_indexes"])]
+    try:
+        from phylign_b200 import _lib
+        from phylign_b200.matcher import Matcher
+        m = Matcher(int(os.environ.get("LOCAL_RANK", 0)))
+        i0 = m.add_synth_index(batch_name(0), _lib.SynthSpec(**specs_kw[0]), w["signature_size"])
+        oidx = oracle_index_from_device(m, i0, w)
+        raw = m.synth_reads([_lib.SynthSpec(**k) for k in specs_kw], READS_SEED, 0, n_sample, w["read_len"],
+                            RANDOM_Q8, ERR_Q16)
+        m.close()
+        built = "index 0 and the reads synthesised on the GPU (setup only), then copied to host RAM"
+    except Exception as e:  # no GPU: build the (small) workload with the oracle itself
+        if w["n_docs"] * w["genome_len"] > 5e7:
+            print(json.dumps({"impl": "reference", "unavailable": f"cannot synthesise the index without a GPU: {e}"}))
+            return
+        ospecs = [oracle.SynthSpec(**k) for k in specs_kw]
+        oidx = oracle.OracleIndex.construct([oracle.synth_genome(ospecs[0], d) for d in range(w["n_docs"])],
+                                            signature_size_override=w["signature_size"])
+        raw = b"".join(oracle.synth_read(ospecs, READS_SEED, r, w["read_len"], RANDOM_Q8, ERR_Q16)
+                       for r in range(n_sample))
+        built = "index 0 and the reads built by the oracle on the CPU"
+    L = w["read_len"]
+    reads = [raw[r * L:(r + 1) * L] for r in range(n_sample)]
+    _, mode_name, _ = time_oracle(oidx, reads[:max(1, n_sample // 8)], cores)  # pick the faster layout
+    mode = 0 if mode_name.startswith("cobs") else 1
+    for _ in range(args.warmup):
+        oidx.query_batch(reads[:max(1, n_sample // 8)], THRESHOLD, threads=cores, mode=mode)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oidx.query_batch(reads, THRESHOLD, threads=cores, mode=mode)
+    dt = (time.perf_counter() - t0) / args.steps
+    # one index timed; the whole database is n_indexes such passes (independent batches)
+    value = n_sample * L / (dt * w["n_indexes"])
+    sample = (f"{n_sample} of the {w['n_reads']} reads against 1 of the {w['n_indexes']} indexes per step "
+              f"({dt:.2f} s), extrapolated x{w['n_indexes']} indexes; CPU restatement of cobs 0.2.1 classic "
+              f"query (oracle port, NOT the cobs binary), layout '{mode_name}'; {built}")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": config_dict(w),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------- GPU arm
+def run_ours(args, w, rank, world, local_rank):
+    from phylign_b200 import _lib
+    from phylign_b200.matcher import Matcher, nccl_unique_id
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("gloo", rank=rank, world_size=world)  # control plane only
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    m = Matcher(local_rank)
+    if world > 1:
+        obj = [nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)
+        m.nccl_init(obj[0], rank, world)
+    specs = [_lib.SynthSpec(**spec_kwargs(i, w)) for i in range(w["n_indexes"])]
+    t_build = time.perf_counter()
+    local = [i for i in range(w["n_indexes"]) if i % world == rank]
+    ids = {i: m.add_synth_index(batch_name(i), specs[i], w["signature_size"]) for i in local}
+    m.sync()
+    t_build = time.perf_counter() - t_build
+    m.set_ranks([batch_name(i) for i in range(w["n_indexes"])])
+    L = w["read_len"]
+    raw = m.synth_reads(specs, READS_SEED, 0, w["n_reads"], L, RANDOM_Q8, ERR_Q16)
+    offs = np.arange(w["n_reads"] + 1, dtype=np.uint64) * L
+    local_alg_bytes = w["n_reads"] * w["kmers_per_read"] * len(local) * w["row_size"]
+
+    # ---- device-resident throughput (`value`): queries already in HBM
+    m.set_queries_raw(raw, offs)
+    for _ in range(args.warmup):
+        m.match_run(THRESHOLD, TOP_N, merge_top_n=TOP_N)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    if dist is not None:
+        import torch
+        torch.cuda.synchronize()
+    m.sync()
+    barrier()
+    launches, gather_ms, phases = 0, [], []
+    m.timer_start()
+    for _ in range(args.steps):
+        m.match_run(THRESHOLD, TOP_N, merge_top_n=TOP_N)
+        ph = m.phase_ms()
+        gather_ms.append(ph[1])
+        phases.append(ph[:3])
+        launches += int(ph[3])
+    dev_ms = m.timer_stop()
+    m.sync()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    dev_ms = max_over_ranks(dev_ms)
+    ms_per_step = dev_ms / args.steps
+    value = w["bases"] / (ms_per_step * 1e-3)
+
+    # ---- end to end through the public API: host buffers in, host results out, every step
+    for _ in range(1):
+        m.set_queries_raw(raw, offs); m.match_run(THRESHOLD, TOP_N, merge_top_n=TOP_N); m.fetch(); m.merged()
+    m.sync()
+    barrier()
+    h2d = d2h = 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        m.set_queries_raw(raw, offs)                       # H2D of the step's inputs
+        m.match_run(THRESHOLD, TOP_N, merge_top_n=TOP_N)
+        res = m.fetch()                                    # D2H: per-(query,index) hit lists (03_match content)
+        moffs, mcands = m.merged()                         # D2H: merged top-N lists (04_filter content)
+        h2d = len(raw) + offs.nbytes
+        d2h = res.d2h_bytes + moffs.nbytes + mcands.nbytes
+    m.sync()
+    e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
+    barrier()
+    e2e_value = w["bases"] / e2e_s
+
+    if rank != 0:
+        m.close()
+        return
+    peak, peak_src = measured_peak()
+    g_ms = float(np.mean(gather_ms))
+    achieved = local_alg_bytes / (g_ms * 1e-3) / 1e9
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": config_dict(w, {"sharding": f"indexes round-robin over {world} GPU(s), queries replicated",
+                                      "index_build_s": round(t_build, 2),
+                                      "kmer_docs_per_s": w["kmer_docs"] / (ms_per_step * 1e-3),
+                                      "phase_ms_hash_gather_merge": [round(float(x), 3) for x in np.mean(phases, axis=0)],
+                                      "n_units": int(len(res.units)), "n_hits": int(len(res.hits)),
+                                      "n_merged": int(len(mcands))}),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None,
+                         "kernel": "gather_count_fused_kernel<32>",
+                         "note": f"algorithmic bytes of rank 0's shard per launch / mean CUDA-event duration of the "
+                                 f"gather phase ({g_ms:.2f} ms, one launch per step); peak = {peak_src}"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": e2e_s * 1e3},
+            "gpu_launches": launches, "clocks": clocks}
+    # ---- CPU baseline beside it (N=1 only): the oracle on the host cores, bounded sample
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            import oracle
+            oracle.build()
+            cores = host_cores()
+            n_sample = min(w["n_reads"], args.cpu_sample_reads)
+            oidx = oracle_index_from_device(m, ids[0], w)
+            reads = [raw[r * L:(r + 1) * L] for r in range(n_sample)]
+            dt, mode_name, both = time_oracle(oidx, reads, cores)
+            v = n_sample * L / (dt * w["n_indexes"])
+            line["cpu_baseline"] = {
+                "value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": f"{n_sample} reads against 1 of the {w['n_indexes']} indexes ({dt:.2f} s), extrapolated "
+                          f"x{w['n_indexes']}; oracle port of cobs 0.2.1 classic query (NOT the cobs binary), "
+                          f"layout '{mode_name}'; both layouts: " +
+                          ", ".join(f"{k}: {t:.2f} s" for k, t in both.items())}
+        except Exception as e:  # the baseline is a report, never a reason to lose the GPU number
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": host_cores(), "kind": "port",
+                                    "sample": f"failed: {e}"}
+    m.close()
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads", type=int, default=100_000)
+    ap.add_argument("--read-len", type=int, default=1000)
+    ap.add_argument("--indexes", type=int, default=64)
+    ap.add_argument("--docs", type=int, default=4000)
+    ap.add_argument("--genome-len", type=int, default=1_000_000)
+    ap.add_argument("--cpu-sample-reads", type=int, default=20_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    args.gpus = max(args.gpus, world)
+    w = workload(args)
+    if args.impl == "reference":
+        run_reference(args, w, rank, world)
+    else:
+        run_ours(args, w, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

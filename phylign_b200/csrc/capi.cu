@@ -462,6 +462,7 @@ extern "C" int phy_match_run(phy_ctx* ctx, const phy_match_params* p, uint32_t m
     PHY_TRY(resident_shape(ctx, &k, &canon, &nh, -1));
     PHY_TRY(phy_sync_indexes(ctx));
     ctx->have_match = ctx->have_merged = false;
+    ctx->hashes_valid = false;  // K1 is part of every match pass (never served from a cache)
     const uint64_t l0 = ctx->launches;
     PHY_CUDA(ctx, cudaEventRecord(ctx->ev_ph[0], ctx->stream));
     PHY_TRY(prepare_hashes(ctx, k, canon, nh));

@@ -119,8 +119,13 @@ __global__ void __launch_bounds__(256) synth_build_kernel(phy_synth_spec s, uint
             uint64_t v = (canonicalize && rc < fwd) ? rc : fwd;
             for (uint32_t j = 0; j < num_hashes; j++) {
                 uint32_t row = phy_fastmod(xxh64_kmer31(v, j), sig, magic);
-                uint64_t bit = (uint64_t)row * stride * 8ull + d;
-                atomicOr(&words[bit >> 5], 1u << (bit & 31));
+                // related genomes share most k-mers: lanes (= neighbouring documents) that hit
+                // the same 32-bit word merge their bits and issue ONE atomic
+                const uint64_t bit = (uint64_t)row * stride * 8ull + d;
+                const unsigned long long word = bit >> 5;
+                const unsigned peers = __match_any_sync(__activemask(), word);
+                const uint32_t m = __reduce_or_sync(peers, 1u << (bit & 31));
+                if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicOr(&words[word], m);
             }
         }
     }
