@@ -45,7 +45,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     procs = []
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [_nvcc(), *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-c",
+        cmd = [_nvcc(), *NVCC_FLAGS, *os.environ.get("PHY_NVCC_DEFS", "").split(), "-I",
+               os.path.join(ROOT, "include"), "-c",
                os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd[1:1] = ["-Xptxas", "-v"]

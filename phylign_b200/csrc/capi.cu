@@ -1,6 +1,7 @@
 // capi.cu -- the C ABI of libphylign_cuda.so (include/phylign_cuda.h): context, HBM
 // accounting, index store, query upload, match driver, result download.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -80,6 +81,8 @@ extern "C" int phy_ctx_create(phy_ctx** out, int device, uint64_t hbm_budget) {
     }
     phy_ctx* ctx = new phy_ctx();
     ctx->device = device;
+    ctx->n_sm = prop.multiProcessorCount;
+    ctx->force_v1 = getenv("PHY_FORCE_V1") && atoi(getenv("PHY_FORCE_V1")) != 0;
     PHY_CUDA(ctx, cudaSetDevice(device));
     size_t fr = 0, tot = 0;
     PHY_CUDA(ctx, cudaMemGetInfo(&fr, &tot));

@@ -185,32 +185,14 @@ struct GatherArgs {
     uint32_t* qcount;
 };
 
-// Fused path: one group of LPR lanes = one (query, index) unit, whole query, whole row.
-template <int LPR>
-__global__ void __launch_bounds__(256, 2) gather_count_fused_kernel(const GatherArgs a) {
-    constexpr int P = PHY_FUSED_PLANES;
-    constexpr int G = 32 / LPR;
-    const int lane = threadIdx.x & 31;
+// Threshold (cobs counts_to_result), top-N + ties (postprocess_cobs.py:21-38) and emission of
+// one (query, index) unit held as vertical counters by a group of LPR lanes.  Bit-sliced:
+// no per-document score is materialised unless the document is kept.
+template <int LPR, int P>
+__device__ __forceinline__ void select_and_emit(const uint32_t (&pl)[P][4], const GatherArgs& a, uint32_t q,
+                                                uint32_t idx_id, uint32_t n_docs, uint32_t nrows, int lane,
+                                                unsigned gm) {
     const int col = lane & (LPR - 1);
-    const unsigned gm = group_mask<LPR>(lane);
-    const uint64_t warp = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const uint64_t gid = warp * G + (lane / LPR);
-    const uint64_t total = (uint64_t)a.n_class_idx * a.n_q;
-    if (gid >= total) return;  // whole groups leave together
-    const uint32_t ipos = (uint32_t)(gid / a.n_q);
-    const uint32_t q = a.qlist[gid - (uint64_t)ipos * a.n_q];
-    const DevIndex& ix = a.indexes[a.class_idx[ipos]];
-    const uint32_t stride = ix.stride, n_docs = ix.n_docs;
-    const uint32_t nrows = a.nk[q];
-
-    uint32_t pl[P][4];
-#pragma unroll
-    for (int p = 0; p < P; p++) pl[p][0] = pl[p][1] = pl[p][2] = pl[p][3] = 0;
-
-    accumulate<LPR, P>(pl, ix.rows + col * 16, (uint32_t)col * 16 < stride, stride, ix.sig, ix.magic,
-                       ix.num_hashes, a.hashes + a.koffs[q], a.total_kmers, nrows, lane, gm);
-
-    // ---- threshold (cobs counts_to_result): score >= T, bit-sliced
     const uint32_t T = a.T[q];
     const uint32_t doc0 = (uint32_t)col * 128u;
     uint32_t pass[4], cnt = 0;
@@ -224,7 +206,7 @@ __global__ void __launch_bounds__(256, 2) gather_count_fused_kernel(const Gather
     const uint32_t n_pass = group_sum<LPR>(cnt, gm);
     if (n_pass == 0) return;
 
-    // ---- top-N + ties (postprocess_cobs.py:21-38): cut = N-th largest score
+    // cut = N-th largest score, found bit by bit from the MSB
     uint32_t n_kept = n_pass;
     if (a.top_n != 0 && n_pass > a.top_n) {
         uint32_t cut = 0;
@@ -245,7 +227,7 @@ __global__ void __launch_bounds__(256, 2) gather_count_fused_kernel(const Gather
         n_kept = group_sum<LPR>(cnt, gm);
     }
 
-    // ---- emit (doc ascending inside the unit; sorted by score later)
+    // emit (doc ascending inside the unit; sorted by score in sort_units_kernel)
     const uint32_t ex = group_exscan<LPR>(cnt, gm, col);
     unsigned long long off = 0;
     if (col == 0) {
@@ -253,7 +235,7 @@ __global__ void __launch_bounds__(256, 2) gather_count_fused_kernel(const Gather
         unsigned long long u = atomicAdd(&a.counters[1], 1ULL);
         if (u < a.units_cap) {
             phy_unit pu;
-            pu.query = q; pu.index = ix.idx_id; pu.n_pass = n_pass; pu.n_kept = n_kept; pu.offset = off;
+            pu.query = q; pu.index = idx_id; pu.n_pass = n_pass; pu.n_kept = n_kept; pu.offset = off;
             a.units[u] = pu;
         }
         atomicAdd(&a.qcount[q], n_kept);
@@ -272,6 +254,189 @@ __global__ void __launch_bounds__(256, 2) gather_count_fused_kernel(const Gather
             h.score = extract_score<P>(pl, w, b);
             *out++ = h;
         }
+    }
+}
+
+// Fused path A (rows narrower than 128 B, or several hash functions): rows go straight
+// from HBM to registers with 8 independent 128-bit loads in flight per lane.
+// One group of LPR lanes = one (query, index) unit, whole query, whole row.
+template <int LPR>
+__global__ void __launch_bounds__(256, 2) gather_count_fused_kernel(const GatherArgs a) {
+    constexpr int P = PHY_FUSED_PLANES;
+    constexpr int G = 32 / LPR;
+    const int lane = threadIdx.x & 31;
+    const int col = lane & (LPR - 1);
+    const unsigned gm = group_mask<LPR>(lane);
+    const uint64_t warp = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint64_t gid = warp * G + (lane / LPR);
+    const uint64_t total = (uint64_t)a.n_class_idx * a.n_q;
+    if (gid >= total) return;  // whole groups leave together
+    const uint32_t ipos = (uint32_t)(gid / a.n_q);
+    const uint32_t q = a.qlist[gid - (uint64_t)ipos * a.n_q];
+    const DevIndex& ix = a.indexes[a.class_idx[ipos]];
+    const uint32_t stride = ix.stride;
+    const uint32_t nrows = a.nk[q];
+
+    uint32_t pl[P][4];
+#pragma unroll
+    for (int p = 0; p < P; p++) pl[p][0] = pl[p][1] = pl[p][2] = pl[p][3] = 0;
+
+    accumulate<LPR, P>(pl, ix.rows + col * 16, (uint32_t)col * 16 < stride, stride, ix.sig, ix.magic,
+                       ix.num_hashes, a.hashes + a.koffs[q], a.total_kmers, nrows, lane, gm);
+    select_and_emit<LPR, P>(pl, a, q, ix.idx_id, ix.n_docs, nrows, lane, gm);
+}
+
+// ---- Fused path B: the HBM-speed kernel for rows of 128-512 B (LPR = 8, 16, 32) ------------
+// The v1 profile (profiles/r01_v1_*) is latency bound: 81% of stall samples wait on the row
+// loads with <= 8 x 512 B in flight per warp.  Here every warp owns a ring of NB batches
+// (8 rows each, 4 KB) in shared memory; rows are fetched with cp.async.bulk (TMA bulk copy,
+// one instruction per row, completion on an mbarrier) NB batches ahead of the carry-save
+// adds, so ~NB*4 KB per warp stay in flight without holding registers.  Warps are
+// persistent and pull (query, index) units from a global counter.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "W: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra W;\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+
+constexpr int BULK_BATCH_BYTES = 4096;  // 8 rows x (32 lanes x 16 B)
+#ifndef PHY_BULK_NB
+#define PHY_BULK_NB 3
+#endif
+#ifndef PHY_BULK_WARPS
+#define PHY_BULK_WARPS 4
+#endif
+constexpr int BULK_NB = PHY_BULK_NB, BULK_WARPS = PHY_BULK_WARPS;
+
+template <int LPR, int NB, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) gather_count_bulk_kernel(const GatherArgs a) {
+    static_assert(LPR >= 8, "bulk path is for row strides >= 128 B");
+    constexpr int P = PHY_FUSED_PLANES;
+    constexpr int G = 32 / LPR;      // units processed side by side by one warp
+    constexpr int BPH = LPR / 8;     // batches per block of LPR hashes
+    constexpr int PITCH = LPR * 16;  // bytes between rows of one group inside a batch
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int col = lane & (LPR - 1), g = lane / LPR;
+    const unsigned gm = group_mask<LPR>(lane);
+    const uint32_t ring = smem_u32(smem) + wid * (NB * BULK_BATCH_BYTES);
+    const uint32_t bars = smem_u32(smem) + WARPS * (NB * BULK_BATCH_BYTES) + wid * (NB * 8);
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NB; i++) mbar_init(bars + i * 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    const uint64_t total = (uint64_t)a.n_class_idx * a.n_q;
+    const uint64_t n_wunits = (total + G - 1) / G;
+    uint32_t jg = 0;  // batches issued so far by this warp == slot/phase bookkeeping
+
+    for (;;) {
+        unsigned long long wu = 0;
+        if (lane == 0) wu = atomicAdd(&a.counters[3], 1ULL);
+        wu = __shfl_sync(FULL, wu, 0);
+        if (wu >= n_wunits) break;
+        const uint64_t gid = wu * G + g;
+        const bool live = gid < total;
+        uint32_t q = 0, nrows = 0, stride = 0, n_docs = 0, idx_id = 0;
+        uint64_t sig = 1, magic = 0;
+        const uint8_t* rows = nullptr;
+        const uint64_t* hq = nullptr;
+        if (live) {
+            const uint32_t ipos = (uint32_t)(gid / a.n_q);
+            q = a.qlist[gid - (uint64_t)ipos * a.n_q];
+            const DevIndex& ix = a.indexes[a.class_idx[ipos]];
+            rows = ix.rows; stride = ix.stride; n_docs = ix.n_docs; idx_id = ix.idx_id;
+            sig = ix.sig; magic = ix.magic;
+            nrows = a.nk[q];
+            hq = a.hashes + a.koffs[q];
+        }
+        uint32_t nmax = nrows;
+#pragma unroll
+        for (int o = 16; o >= LPR; o >>= 1) nmax = max(nmax, __shfl_xor_sync(FULL, nmax, o));
+        const uint32_t nb = (nmax + 7) >> 3;  // warp-uniform number of batches
+        const bool lane_on = (uint32_t)col * 16u < stride;
+
+        uint32_t pl[P][4];
+#pragma unroll
+        for (int p = 0; p < P; p++) pl[p][0] = pl[p][1] = pl[p][2] = pl[p][3] = 0;
+
+        uint32_t myrow = PHY_ROW_INVALID;
+        uint64_t hnext = (uint32_t)col < nrows ? __ldg(hq + col) : 0;  // hashes of block 0
+        const uint32_t j0 = jg;
+        auto issue = [&](uint32_t j) {  // j = batch number inside this unit
+            const uint32_t hb = j / BPH, s = j % BPH;
+            if (s == 0) {
+                const uint32_t hidx = hb * LPR + col;
+                myrow = hidx < nrows ? phy_fastmod(hnext, sig, magic) : PHY_ROW_INVALID;
+                const uint32_t hn = hidx + LPR;
+                hnext = hn < nrows ? __ldg(hq + hn) : 0;  // prefetch the next block's hashes
+            }
+            const bool mine = (uint32_t)(col >> 3) == s && myrow != PHY_ROW_INVALID;
+            const unsigned bal = __ballot_sync(FULL, mine);
+            const uint32_t slot = (j0 + j) % NB;
+            const uint32_t bar = bars + slot * 8;
+            if (lane == 0) mbar_expect_tx(bar, (uint32_t)__popc(bal) * stride);
+            if (mine)
+                bulk_g2s(ring + slot * BULK_BATCH_BYTES + (g * 8 + (col & 7)) * PITCH,
+                         rows + (uint64_t)myrow * stride, stride, bar);
+        };
+        const uint32_t npro = nb < (uint32_t)NB ? nb : (uint32_t)NB;
+        for (uint32_t j = 0; j < npro; j++) issue(j);
+        for (uint32_t j = 0; j < nb; j++) {
+            const uint32_t slot = (j0 + j) % NB;
+            mbar_wait(bars + slot * 8, ((j0 + j) / NB) & 1u);
+            const uint32_t src = ring + slot * BULK_BATCH_BYTES + g * 8 * PITCH + col * 16;
+            uint4 v[8];
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                if (j * 8 + r < nrows && lane_on) v[r] = lds128(src + r * PITCH);
+                else v[r] = make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int w = 0; w < 4; w++) {
+                auto W = [&](const uint4& x) -> uint32_t {
+                    return w == 0 ? x.x : (w == 1 ? x.y : (w == 2 ? x.z : x.w));
+                };
+                uint32_t twoA, twoB, fourA, fourB, eight;
+                csa(twoA, pl[0][w], pl[0][w], W(v[0]), W(v[1]));
+                csa(twoB, pl[0][w], pl[0][w], W(v[2]), W(v[3]));
+                csa(fourA, pl[1][w], pl[1][w], twoA, twoB);
+                csa(twoA, pl[0][w], pl[0][w], W(v[4]), W(v[5]));
+                csa(twoB, pl[0][w], pl[0][w], W(v[6]), W(v[7]));
+                csa(fourB, pl[1][w], pl[1][w], twoA, twoB);
+                csa(eight, pl[2][w], pl[2][w], fourA, fourB);
+                uint32_t carry = eight;
+#pragma unroll
+                for (int p = 3; p < P; p++) {
+                    uint32_t t = pl[p][w] & carry;
+                    pl[p][w] ^= carry;
+                    carry = t;
+                }
+            }
+            __syncwarp();  // every lane has consumed the slot before it is refilled
+            if (j + NB < nb) issue(j + NB);
+        }
+        jg = j0 + nb;
+        if (live) select_and_emit<LPR, P>(pl, a, q, idx_id, n_docs, nrows, lane, gm);
+        __syncwarp();
     }
 }
 
@@ -405,6 +570,25 @@ void launch_fused(const GatherArgs& a, cudaStream_t st) {
     if (blocks) gather_count_fused_kernel<LPR><<<blocks, 256, 0, st>>>(a);
 }
 
+template <int LPR, int NB, int WARPS>
+int launch_bulk(const GatherArgs& a, cudaStream_t st, int n_sm) {
+    constexpr int SMEM = WARPS * NB * BULK_BATCH_BYTES + WARPS * NB * 8;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(gather_count_bulk_kernel<LPR, NB, WARPS>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) return -1;
+        configured = true;
+    }
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gather_count_bulk_kernel<LPR, NB, WARPS>,
+                                                      WARPS * 32, SMEM) != cudaSuccess || per_sm < 1) return -1;
+    constexpr int G = 32 / LPR;
+    uint64_t wunits = ((uint64_t)a.n_class_idx * a.n_q + G - 1) / G;
+    uint64_t blocks = std::min<uint64_t>((wunits + WARPS - 1) / WARPS, (uint64_t)n_sm * per_sm);
+    if (blocks) gather_count_bulk_kernel<LPR, NB, WARPS><<<(unsigned)blocks, WARPS * 32, SMEM, st>>>(a);
+    return 0;
+}
+
 template <int LPR>
 void launch_accum(const DevIndex* ixp, const SlowItem* items, uint32_t n_items, uint32_t n_chunks,
                   const uint64_t* koffs, const uint64_t* hashes, uint64_t total_kmers,
@@ -531,7 +715,20 @@ int phy_launch_gather(phy_ctx* ctx, const phy_match_params* p) {
                 if (cls[c].empty()) continue;
                 a.class_idx = d_class + class_off[c];
                 a.n_class_idx = (uint32_t)cls[c].size();
-                switch (c) {
+                bool multi_hash = false;
+                for (uint32_t i : cls[c]) multi_hash |= ctx->idx[i].d.num_hashes > 1;
+                const bool bulk = c >= 3 && !multi_hash && !ctx->force_v1;
+                if (bulk) {  // persistent warps pull units from counters[3]
+                    PHY_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p + 3, 0, sizeof(unsigned long long), ctx->stream));
+                    int rc = c == 3 ? launch_bulk<8, BULK_NB, BULK_WARPS>(a, ctx->stream, ctx->n_sm)
+                           : c == 4 ? launch_bulk<16, BULK_NB, BULK_WARPS>(a, ctx->stream, ctx->n_sm)
+                                    : launch_bulk<32, BULK_NB, BULK_WARPS>(a, ctx->stream, ctx->n_sm);
+                    if (rc != 0) {
+                        phy_set_error(ctx, "cannot configure the bulk gather kernel: %s",
+                                      cudaGetErrorString(cudaGetLastError()));
+                        return PHY_ERR_CUDA;
+                    }
+                } else switch (c) {
                     case 0: launch_fused<1>(a, ctx->stream); break;
                     case 1: launch_fused<2>(a, ctx->stream); break;
                     case 2: launch_fused<4>(a, ctx->stream); break;
