@@ -6,7 +6,7 @@
  *   scripts/run_cobs_streaming.sh:24-29, Snakefile:419-424, Snakefile:476-481
  *       `cobs query --load-complete -t THR -T N -i INDEX -f QUERIES`   -> phy_index_* + phy_match
  *   scripts/postprocess_cobs.py:21-38   per-batch top-N + ties          -> phy_match (top_n)
- *   scripts/filter_queries.py:105-156   global top-N + ties over batches -> phy_merge_topn
+ *   scripts/filter_queries.py:105-156   global top-N + ties over batches -> phy_match_run(merge_top_n) + phy_merged_fetch, phy_merge_host
  *
  * Conventions: plain pointers and sizes only; every function returns PHY_OK (0)
  * or a negative status and leaves a message retrievable with phy_last_error();
@@ -138,6 +138,12 @@ typedef struct phy_merged {
  * an empty list with n_queries set). */
 int phy_merged_fetch(phy_ctx* ctx, phy_merged** out);
 void phy_merged_free(phy_merged* m);
+/* Merge candidates that come from the host (the `filter_queries.py -n N -q fa match files...`
+ * entry: match files parsed by the driver): cands[offs[q] .. offs[q+1]) belong to query q;
+ * score, batch_rank (<4096) and ref_rank (<2^20) form the sort key, doc is carried along.
+ * Result via phy_merged_fetch.  Single GPU. */
+int phy_merge_host(phy_ctx* ctx, uint32_t n_queries, uint32_t top_n, const uint64_t* offs,
+                   const phy_cand* cands);
 
 /* ------------------------------------------------------------------- multi-GPU */
 #define PHY_NCCL_ID_BYTES 128

@@ -90,6 +90,7 @@ PROTOTYPES = {
     "phy_scores": (C.c_int, [_P, C.c_int, C.c_void_p]),
     "phy_merged_fetch": (C.c_int, [_P, C.POINTER(C.POINTER(Merged))]),
     "phy_merged_free": (None, [C.POINTER(Merged)]),
+    "phy_merge_host": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
     "phy_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "phy_nccl_init": (C.c_int, [_P, C.c_void_p, C.c_int, C.c_int]),
     "phy_timer_start": (C.c_int, [_P]),

@@ -1,0 +1,288 @@
+"""Command-line drop-ins for the reference's match-stage commands.
+
+    python -m phylign_b200.cli cobs query [--load-complete] -t THR -T N -i INDEX
+                                          [--index-sizes BYTES] -f QUERY.fa
+        same flags and stdout protocol as the `cobs query` call of
+        /root/reference/scripts/run_cobs_streaming.sh:24-29 and Snakefile:419-424,476-481
+        (-T is accepted and ignored: the GPU replaces the thread pool)
+    python -m phylign_b200.cli run-cobs-streaming THR THREADS INDEX.xz SIZE QUERY.fa
+        the 5 positionals of scripts/run_cobs_streaming.sh:13-22
+    python -m phylign_b200.cli postprocess -n N           (stdin -> stdout)
+        scripts/postprocess_cobs.py:42-58
+    python -m phylign_b200.cli filter -n N -q QUERY.fa MATCH.gz [MATCH.gz ...]
+        scripts/filter_queries.py:209-238 (merge on the GPU, FASTA on stdout, log on stderr)
+    python -m phylign_b200.cli match-db --cobs-dir DIR --batches FILE -q QUERY.fa
+                                        --match-dir intermediate/03_match --filter-out OUT.fa
+        all batches in one resident context: writes every {batch}____{qfile}.gz and the
+        04_filter FASTA (replaces 305 `decompress_and_run_cobs` jobs + `translate_matches`)
+
+Any failure exits non-zero and leaves nothing partial at the output paths (the rules run
+under `set -euo pipefail`, Snakefile:142).
+"""
+from __future__ import annotations
+
+import argparse
+import gzip
+import os
+import sys
+
+import numpy as np
+
+from . import fasta
+from .cobs_index import ref_of
+from .cobs_text import format_cobs_text, format_filter_fasta
+
+
+def _die(msg, code=1):
+    print(f"phylign_b200: error: {msg}", file=sys.stderr)
+    sys.exit(code)
+
+
+def _postprocess_stream(fin, fout, keep: int):
+    """Text filter with the exact semantics of postprocess_cobs.py:21-38."""
+    i, min_kmers = 0, 0
+    for x in fin:
+        if x[0] == "*":
+            i, min_kmers = 0, 0
+            fout.write(x)
+            continue
+        y = "_" + x.partition("_")[2]
+        i += 1
+        if i < keep:
+            fout.write(y)
+        elif i == keep:
+            fout.write(y)
+            min_kmers = int(y.split("\t")[-1])
+        elif int(y.split("\t")[-1]) == min_kmers:
+            fout.write(y)
+
+
+# ------------------------------------------------------------------------------------ cobs query
+def cmd_cobs_query(a):
+    from .matcher import Matcher
+    records = fasta.read_cobs_records(a.f)
+    with Matcher(a.device) as m:
+        idx = m.load_index(a.i, batch="index")
+        hdr = m.indexes[idx].header
+        if a.index_sizes is not None and a.index_sizes != hdr.header_size + hdr.body_size:
+            _die(f"--index-sizes {a.index_sizes} != header {hdr.header_size} + body {hdr.body_size}")
+        m.set_queries(records)
+        res = m.match(a.t, top_n=a.top_n, floor_mode=a.floor)
+        sys.stdout.write(format_cobs_text(records, res, m.indexes[idx], strip_prefix=a.top_n > 0))
+    sys.stdout.flush()
+
+
+# ------------------------------------------------------------------------------------ filter
+def parse_match_file(path):
+    """[(qname, [(ref, kmers)])] with the parsing rules of filter_queries.py:27-66."""
+    blocks = []
+    opener = gzip.open if str(path).endswith(".gz") else open
+    with opener(path, "rt") as f:
+        for x in f:
+            x = x.strip()
+            if not x:
+                continue
+            if x[0] == "*":
+                parts = x[1:].split("\t")
+                int(parts[1])
+                blocks.append((parts[0].split(" ")[0], []))
+            else:
+                if not blocks:
+                    raise ValueError(f"{path}: hit line before any query header")
+                tmp_name, kmers = x.split()
+                _rid, ref = tmp_name.split("_")       # exactly one underscore (filter_queries.py:64)
+                blocks[-1][1].append((ref, int(kmers)))
+    if not blocks:
+        raise ValueError(f"{path}: empty match file")
+    return blocks
+
+
+def merge_match_files(m, query_fn, match_fns, keep: int, log=sys.stderr) -> str:
+    """filter_queries.py process_files on the GPU (phy_merge_host)."""
+    from .matcher import CAND_DT
+    queries = {}
+    for qname, seq in fasta.read_fastx(query_fn):
+        queries[qname] = seq                      # duplicate names overwrite, first position kept
+    qid = {q: i for i, q in enumerate(queries)}
+    per_batch = []
+    for fn in match_fns:
+        batch = os.path.basename(fn).split("____")[0]
+        print(f"Translating matches {fn}", file=log)
+        per_batch.append((batch, parse_match_file(fn)))
+    batch_names = sorted({b for b, _ in per_batch})
+    brank = {b: i for i, b in enumerate(batch_names)}
+    refs_sorted = {b: sorted({ref for bb, blocks in per_batch if bb == b for _, hits in blocks for ref, _ in hits})
+                   for b in batch_names}
+    rrank = {b: {r: i for i, r in enumerate(refs_sorted[b])} for b in batch_names}
+    rows = [[] for _ in queries]
+    for batch, blocks in per_batch:
+        br, rr = brank[batch], rrank[batch]
+        for qname, hits in blocks:
+            if qname not in qid:
+                raise KeyError(f"query {qname!r} of batch {batch} is not in {query_fn}")
+            rows[qid[qname]].extend((k, br, rr[ref], rr[ref]) for ref, k in hits)
+    offs = np.zeros(len(rows) + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum([len(r) for r in rows], dtype=np.uint64)
+    flat = [t for r in rows for t in r]
+    cands = np.array(flat, dtype=CAND_DT) if flat else np.zeros(0, CAND_DT)
+    moffs, mc = m.merge_host(offs, cands, keep)
+    refs_by_rank = {brank[b]: refs_sorted[b] for b in batch_names}
+    return format_filter_fasta(list(queries.items()), moffs, mc, refs_by_rank)
+
+
+def cmd_filter(a):
+    from .matcher import Matcher
+    with Matcher(a.device) as m:
+        out = merge_match_files(m, a.query_fn, a.match_fn, a.keep)
+    sys.stdout.write(out)
+    sys.stdout.flush()
+
+
+# ------------------------------------------------------------------------------------ whole database
+def _atomic_write(path, data: bytes, gz: bool):
+    tmp = f"{path}.tmp.{os.getpid()}"
+    try:
+        if gz:
+            with gzip.GzipFile(tmp, "wb", compresslevel=1, mtime=0) as f:
+                f.write(data)
+        else:
+            with open(tmp, "wb") as f:
+                f.write(data)
+        os.replace(tmp, path)
+    finally:
+        if os.path.exists(tmp):
+            os.unlink(tmp)
+
+
+def cmd_match_db(a):
+    from .matcher import Matcher
+    with open(a.batches) as f:
+        batches = sorted(filter(len, map(str.strip, f)))      # Snakefile:32-34
+    records = fasta.read_cobs_records(a.q)
+    qfile = a.qfile or os.path.splitext(os.path.basename(a.q))[0]
+    os.makedirs(a.match_dir, exist_ok=True)
+    sizes = {}
+    if a.index_sizes_table:
+        with open(a.index_sizes_table) as f:
+            for line in f:
+                p = line.split()
+                if len(p) >= 2:
+                    sizes[os.path.basename(p[0]).replace(".cobs_classic.xz", "")] = int(p[1])
+    merged_inputs = []
+    with Matcher(a.device, a.hbm_budget) as m:
+        m.set_queries(records)
+        pending = list(batches)
+        while pending:
+            loaded = []
+            while pending:                                    # fill HBM, then run, then evict
+                b = pending[0]
+                path = os.path.join(a.cobs_dir, f"{b}.cobs_classic.xz")
+                if not os.path.exists(path):
+                    path = path[:-3]
+                out = os.path.join(a.match_dir, f"{b}____{qfile}.gz")
+                if a.resume and os.path.exists(out):          # file-granular resume like Snakemake
+                    pending.pop(0)
+                    merged_inputs.append(out)
+                    continue
+                try:
+                    idx = m.load_index(path, batch=b)
+                except Exception as e:
+                    if loaded and "PHY_ERR_NOMEM" in str(e):
+                        break                                  # does not fit beside the others: next round
+                    raise
+                hdr = m.indexes[idx].header
+                if b in sizes and sizes[b] != hdr.header_size + hdr.body_size:
+                    _die(f"{b}: decompressed size {hdr.header_size + hdr.body_size} != table {sizes[b]}")
+                loaded.append(idx)
+                pending.pop(0)
+            if not loaded:
+                continue
+            res = m.match(a.t, top_n=a.n, floor_mode=a.floor)
+            for idx in loaded:
+                ix = m.indexes[idx]
+                text = format_cobs_text(records, res, ix, strip_prefix=True)
+                out = os.path.join(a.match_dir, f"{ix.batch}____{qfile}.gz")
+                _atomic_write(out, text.encode(), gz=True)
+                merged_inputs.append(out)
+                print(f"[match-db] {ix.batch}: {len(res.units_of(idx))} queries with hits", file=sys.stderr)
+            for idx in loaded:
+                m.evict(idx)
+        if a.filter_out:
+            fa = merge_match_files(m, a.q, sorted(merged_inputs), a.n, log=open(os.devnull, "w"))
+            os.makedirs(os.path.dirname(os.path.abspath(a.filter_out)), exist_ok=True)
+            _atomic_write(a.filter_out, fa.encode(), gz=False)
+
+
+# ------------------------------------------------------------------------------------ argparse
+def build_parser():
+    ap = argparse.ArgumentParser(prog="phylign_b200", description=__doc__,
+                                 formatter_class=argparse.RawDescriptionHelpFormatter)
+    sub = ap.add_subparsers(dest="cmd", required=True)
+
+    cobs = sub.add_parser("cobs", help="cobs-compatible front end").add_subparsers(dest="cobs_cmd", required=True)
+    q = cobs.add_parser("query")
+    q.add_argument("--load-complete", action="store_true", help="accepted for compatibility (always resident in HBM)")
+    q.add_argument("-t", type=float, default=0.8, help="k-mer threshold (cobs default 0.8)")
+    q.add_argument("-T", type=int, default=0, help="threads: accepted and ignored")
+    q.add_argument("-i", required=True, help="index file (.cobs_classic, .cobs_classic.xz or a pipe)")
+    q.add_argument("--index-sizes", type=int, default=None, help="decompressed index size in bytes (verified)")
+    q.add_argument("-f", required=True, help="query FASTA")
+    q.add_argument("--top-n", type=int, default=0, help="fuse postprocess_cobs.py -n N (names get the '_acc' form)")
+    q.add_argument("--floor", action="store_true", help="threshold = floor(t*K) instead of ceil (SURVEY A.6)")
+    q.add_argument("--device", type=int, default=0)
+    q.set_defaults(fn=cmd_cobs_query)
+
+    r = sub.add_parser("run-cobs-streaming")
+    r.add_argument("kmer_thres", type=float)
+    r.add_argument("threads")
+    r.add_argument("cobs_index_xz")
+    r.add_argument("uncompressed_size", type=int)
+    r.add_argument("query")
+    r.add_argument("--device", type=int, default=0)
+    r.set_defaults(fn=lambda a: cmd_cobs_query(argparse.Namespace(
+        t=a.kmer_thres, T=0, i=a.cobs_index_xz, index_sizes=a.uncompressed_size, f=a.query, top_n=0,
+        floor=False, device=a.device)))
+
+    p = sub.add_parser("postprocess")
+    p.add_argument("-n", dest="keep", required=True, type=int, metavar="int", help="no. of best hits to keep")
+    p.set_defaults(fn=lambda a: _postprocess_stream(sys.stdin, sys.stdout, a.keep))
+
+    f = sub.add_parser("filter")
+    f.add_argument("match_fn", nargs="+")
+    f.add_argument("-q", dest="query_fn", required=True, metavar="str", help="query file")
+    f.add_argument("-n", dest="keep", type=int, default=100, metavar="int", help="no. of best hits to keep [100]")
+    f.add_argument("--device", type=int, default=0)
+    f.set_defaults(fn=cmd_filter)
+
+    d = sub.add_parser("match-db")
+    d.add_argument("--cobs-dir", required=True)
+    d.add_argument("--batches", required=True, help="file with one batch name per line (config.yaml: batches)")
+    d.add_argument("-q", required=True, help="merged query FASTA (intermediate/01_queries_merged/{qfile}.fa)")
+    d.add_argument("--qfile", default=None, help="qfile wildcard (default: stem of -q)")
+    d.add_argument("--match-dir", default="intermediate/03_match")
+    d.add_argument("--filter-out", default=None, help="intermediate/04_filter/{qfile}.fa")
+    d.add_argument("-t", type=float, default=0.7, help="cobs_kmer_thres")
+    d.add_argument("-n", type=int, default=100, help="nb_best_hits")
+    d.add_argument("--floor", action="store_true")
+    d.add_argument("--index-sizes-table", default=None, help="data/decompressed_indexes_sizes.txt (verified)")
+    d.add_argument("--resume", action="store_true", help="skip batches whose match file exists")
+    d.add_argument("--hbm-budget", type=int, default=0)
+    d.add_argument("--device", type=int, default=0)
+    d.set_defaults(fn=cmd_match_db)
+    return ap
+
+
+def main(argv=None):
+    a = build_parser().parse_args(argv)
+    try:
+        a.fn(a)
+    except SystemExit:
+        raise
+    except BrokenPipeError:
+        sys.exit(1)
+    except Exception as e:           # one line on stderr, non-zero exit (set -euo pipefail callers)
+        _die(f"{type(e).__name__}: {e}")
+
+
+if __name__ == "__main__":
+    main()

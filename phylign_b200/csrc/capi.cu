@@ -593,6 +593,34 @@ extern "C" int phy_merged_fetch(phy_ctx* ctx, phy_merged** out) {
     return PHY_OK;
 }
 
+int phy_merge_host_impl(phy_ctx* ctx, uint32_t nq, uint32_t top_n, const uint64_t* offs, const phy_cand* cands);
+
+extern "C" int phy_merge_host(phy_ctx* ctx, uint32_t n_queries, uint32_t top_n, const uint64_t* offs,
+                              const phy_cand* cands) {
+    if (!ctx || !offs || (!cands && offs[n_queries])) return PHY_ERR_ARG;
+    if (ctx->n_ranks > 1) {
+        phy_set_error(ctx, "phy_merge_host is a single-GPU entry point");
+        return PHY_ERR_STATE;
+    }
+    for (uint32_t q = 0; q < n_queries; q++)
+        if (offs[q + 1] < offs[q]) {
+            phy_set_error(ctx, "candidate offsets must be non-decreasing");
+            return PHY_ERR_ARG;
+        }
+    for (uint64_t i = 0; i < offs[n_queries]; i++)
+        if (cands[i].batch_rank >= PHY_MAX_BATCH_RANK || cands[i].ref_rank >= PHY_MAX_DOCS) {
+            phy_set_error(ctx, "candidate %llu: rank out of range", (unsigned long long)i);
+            return PHY_ERR_ARG;
+        }
+    PHY_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->have_queries = ctx->have_match = false;  // the query set of this ctx is replaced
+    ctx->have_merged = false;
+    PHY_TRY(phy_merge_host_impl(ctx, n_queries, top_n, offs, cands));
+    PHY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->have_merged = true;
+    return PHY_OK;
+}
+
 extern "C" void phy_merged_free(phy_merged* m) {
     if (!m) return;
     free(m->offs);

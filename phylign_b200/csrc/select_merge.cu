@@ -217,7 +217,35 @@ __global__ void __launch_bounds__(256) compact_final_kernel(const uint64_t* __re
     }
 }
 
+__global__ void __launch_bounds__(256) cands_to_keys_kernel(const phy_cand* __restrict__ c, uint64_t n,
+                                                            uint64_t* __restrict__ ckey, uint32_t* __restrict__ cval) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        phy_cand x = c[i];
+        ckey[i] = ((uint64_t)(~x.score) << 32) | ((uint64_t)(x.batch_rank & 0xFFFu) << 20) | (x.ref_rank & 0xFFFFFu);
+        cval[i] = x.doc;
+    }
+}
+
 }  // namespace
+
+// candidates supplied by the host, already grouped per query (offs[nq+1])
+int phy_merge_host_impl(phy_ctx* ctx, uint32_t nq, uint32_t top_n, const uint64_t* offs, const phy_cand* cands) {
+    const uint64_t total = offs[nq];
+    ctx->nq = nq;
+    PHY_TRY(phy_ensure(ctx, ctx->d_qoffs_c, nq + 2));
+    PHY_TRY(phy_h2d(ctx, ctx->d_qoffs_c.p, offs, ((size_t)nq + 1) * sizeof(uint64_t)));
+    PHY_TRY(phy_ensure(ctx, ctx->d_ckey, total + 1));
+    PHY_TRY(phy_ensure(ctx, ctx->d_cval, total + 1));
+    PHY_TRY(phy_ensure(ctx, ctx->d_recv, total + 1));
+    if (total) {
+        PHY_TRY(phy_h2d(ctx, ctx->d_recv.p, cands, total * sizeof(phy_cand)));
+        unsigned blocks = (unsigned)std::min<uint64_t>((total + 255) / 256, 148ull * 16);
+        cands_to_keys_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_recv.p, total, ctx->d_ckey.p, ctx->d_cval.p);
+        ctx->launches++;
+        PHY_CUDA(ctx, cudaGetLastError());
+    }
+    return phy_merge_segments(ctx, top_n);
+}
 
 // out must hold n+1 entries; *total_host receives out[n]
 int phy_exscan(phy_ctx* ctx, const uint32_t* d_in, uint64_t n, uint64_t* d_out, uint64_t* total_host) {

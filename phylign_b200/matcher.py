@@ -223,6 +223,14 @@ class Matcher:
         finally:
             self._L.phy_merged_free(mp)
 
+    def merge_host(self, offs: np.ndarray, cands: np.ndarray, top_n: int):
+        """filter_queries.py entry: merge host-supplied candidates (CAND_DT, grouped by query)."""
+        offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        cands = np.ascontiguousarray(cands, dtype=CAND_DT)
+        self._ck(self._L.phy_merge_host(self._ctx, len(offs) - 1, int(top_n), offs.ctypes.data,
+                                        cands.ctypes.data))
+        return self.merged()
+
     def scores(self, idx_id) -> np.ndarray:
         nq = len(self._seq_keepalive[1]) - 1
         d = self.indexes[idx_id].header.n_docs

@@ -1,0 +1,75 @@
+"""The command-line drop-ins end to end on the GPU, against the golden vectors."""
+import gzip
+import os
+import subprocess
+import sys
+
+import pytest
+
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ENV = dict(os.environ, PYTHONPATH=ROOT)
+
+
+def _run(args, **kw):
+    return subprocess.run(args, capture_output=True, text=True, env=ENV, cwd=ROOT, **kw)
+
+
+@pytest.mark.parametrize("batch", H.GOLDEN_BATCHES)
+def test_run_cobs_streaming_dropin(batch):
+    xz = os.path.join(H.GOLDEN, f"{batch}.cobs_classic.xz")
+    size = len(H.golden_index_bytes(batch))
+    r = _run([os.path.join(ROOT, "scripts", "run_cobs_streaming.sh"), "0.7", "4", xz, str(size),
+              os.path.join(H.GOLDEN, "queries.fa")])
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == H.golden_cobs_text(batch)
+    # wrong --index-sizes must fail loudly
+    r = _run([os.path.join(ROOT, "scripts", "run_cobs_streaming.sh"), "0.7", "4", xz, str(size + 1),
+              os.path.join(H.GOLDEN, "queries.fa")])
+    assert r.returncode != 0 and "index-sizes" in r.stderr
+
+
+def test_cobs_query_reads_index_from_pipe_and_feeds_reference_postprocess(tmp_path):
+    """`cobs query -i <(xzcat ...)` exactly as run_cobs_streaming.sh:24-29 spells it."""
+    batch = "bbb__02"
+    xz = os.path.join(H.GOLDEN, f"{batch}.cobs_classic.xz")
+    cmd = (f"{ROOT}/scripts/cobs query --load-complete -t 0.7 -T 8 "
+           f"-i <(xzcat --no-sparse --ignore-check {xz}) --index-sizes {len(H.golden_index_bytes(batch))} "
+           f"-f {H.GOLDEN}/queries.fa | {sys.executable} -m phylign_b200.cli postprocess -n 3")
+    r = _run(["bash", "-o", "pipefail", "-c", cmd])
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == H.golden_match_text(batch, 3)
+    r2 = _run([f"{ROOT}/scripts/cobs", "query", "-t", "0.7", "-i", xz, "-f", f"{H.GOLDEN}/queries.fa",
+               "--top-n", "3"])
+    assert r2.returncode == 0 and r2.stdout == H.golden_match_text(batch, 3)
+
+
+@pytest.mark.parametrize("keep", [1, 3, 100])
+def test_filter_dropin_on_reference_match_files(keep):
+    files = [os.path.join(H.GOLDEN, f"n{keep}", f"{b}____queries.gz") for b in H.GOLDEN_BATCHES]
+    r = _run([sys.executable, os.path.join(ROOT, "scripts", "filter_queries_gpu.py"), "-n", str(keep),
+              "-q", os.path.join(H.GOLDEN, "queries.fa")] + files[::-1])
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == H.golden_filter_fa(keep)
+
+
+def test_match_db_writes_all_rule_outputs(tmp_path):
+    batches = tmp_path / "batches.txt"
+    batches.write_text("\n".join(reversed(H.GOLDEN_BATCHES)) + "\n\n")
+    mdir, out = tmp_path / "03_match", tmp_path / "04_filter" / "queries.fa"
+    r = _run([sys.executable, "-m", "phylign_b200.cli", "match-db", "--cobs-dir", H.GOLDEN, "--batches",
+              str(batches), "-q", os.path.join(H.GOLDEN, "queries.fa"), "--match-dir", str(mdir),
+              "--filter-out", str(out), "-t", "0.7", "-n", "3"])
+    assert r.returncode == 0, r.stderr
+    for b in H.GOLDEN_BATCHES:
+        got = gzip.open(mdir / f"{b}____queries.gz", "rt").read()
+        assert got == H.golden_match_text(b, 3)
+    assert out.read_text() == H.golden_filter_fa(3)
+    assert not [f for f in os.listdir(mdir) if ".tmp." in f]
+    # a missing batch fails, and leaves no partial file behind
+    batches.write_text("nosuch__01\n")
+    r = _run([sys.executable, "-m", "phylign_b200.cli", "match-db", "--cobs-dir", H.GOLDEN, "--batches",
+              str(batches), "-q", os.path.join(H.GOLDEN, "queries.fa"), "--match-dir", str(tmp_path / "x")])
+    assert r.returncode != 0 and not os.listdir(tmp_path / "x")

@@ -111,3 +111,39 @@ def test_text_formatters_with_synthetic_results():
     refs = {0: ["SAMEB3", "SAMEB5"], 1: ["SAMEA3", "SAMEA1", "SAMEA5"]}
     got = format_filter_fasta([("q1", "AC"), ("q2", "GT"), ("q3", "TT")], offs, cands, refs)
     assert got == ">q1 SAMEB3,SAMEA1,SAMEA3\nAC\n>q2 \nGT\n>q3 SAMEB5,SAMEA5\nTT\n"
+
+
+@pytest.mark.parametrize("keep", [1, 3, 100])
+def test_cli_postprocess_stream_equals_reference_output(keep):
+    """`phylign_b200.cli postprocess -n N` == unmodified postprocess_cobs.py (golden files)."""
+    import io
+    from phylign_b200.cli import _postprocess_stream
+    for batch in H.GOLDEN_BATCHES:
+        out = io.StringIO()
+        _postprocess_stream(io.StringIO(H.golden_cobs_text(batch)), out, keep)
+        assert out.getvalue() == H.golden_match_text(batch, keep)
+
+
+def test_cli_parse_match_file_rules(tmp_path):
+    from phylign_b200.cli import parse_match_file
+    p = os.path.join(H.GOLDEN, "n3", "aaa__01____queries.gz")
+    blocks = parse_match_file(p)
+    ref = H.read_fasta(os.path.join(H.GOLDEN, "queries.fa"))
+    assert [q for q, _ in blocks] == [h.split(" ")[0] for h, _ in ref]
+    bad = tmp_path / "b__01____q.gz"
+    with gzip.open(bad, "wt") as f:
+        f.write("*q1\t1\nno_under_score_name\t5\n")
+    with pytest.raises(ValueError):
+        parse_match_file(str(bad))          # filter_queries.py:64 raises on a second underscore too
+    empty = tmp_path / "e__01____q.gz"
+    with gzip.open(empty, "wt") as f:
+        f.write("")
+    with pytest.raises(ValueError):
+        parse_match_file(str(empty))
+
+
+def test_run_cobs_streaming_usage_error():
+    import subprocess
+    r = subprocess.run([os.path.join(ROOT, "scripts", "run_cobs_streaming.sh"), "0.7", "1"],
+                       capture_output=True, text=True)
+    assert r.returncode == 1 and "usage:" in r.stderr and "kmer_thres threads cobs_index.xz" in r.stderr
