@@ -1,0 +1,64 @@
+"""Two-GPU parity of the NCCL merge (skipped on a single-GPU box)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import os, sys, time
+root, rank, world, idfile, keep, out = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), sys.argv[4], int(sys.argv[5]), sys.argv[6]
+sys.path.insert(0, root)
+from phylign_b200.matcher import Matcher, nccl_unique_id
+from phylign_b200.cobs_index import ref_of
+from phylign_b200.cobs_text import format_filter_fasta
+from tests import helpers as H
+if rank == 0:
+    with open(idfile + ".tmp", "wb") as f: f.write(nccl_unique_id())
+    os.replace(idfile + ".tmp", idfile)
+while not os.path.exists(idfile): time.sleep(0.05)
+m = Matcher(rank)
+m.nccl_init(open(idfile, "rb").read(), rank, world)
+mine = [b for i, b in enumerate(H.GOLDEN_BATCHES) if i % world == rank]
+for b in mine: m.load_index(os.path.join(H.GOLDEN, b + ".cobs_classic.xz"))
+m.set_ranks(H.GOLDEN_BATCHES)
+qs = H.read_fasta(os.path.join(H.GOLDEN, "queries.fa"))
+m.set_queries(qs)
+m.match_run(0.7, top_n=keep, merge_top_n=keep)
+offs, cands = m.merged()
+if rank == 0:
+    import lzma
+    from phylign_b200.cobs_index import parse_bytes
+    refs = {}
+    for r, b in enumerate(sorted(H.GOLDEN_BATCHES)):
+        hdr, _ = parse_bytes(H.golden_index_bytes(b))
+        refs[r] = [ref_of(n) for n in hdr.doc_names]
+    open(out, "w").write(format_filter_fasta([(h.split(" ")[0], s) for h, s in qs], offs, cands, refs))
+else:
+    assert len(cands) == 0
+m.close()
+'''
+
+
+@pytest.mark.parametrize("keep", [1, 100])
+def test_two_gpu_nccl_merge_equals_reference_filter(tmp_path, keep):
+    import ctypes as C
+    from phylign_b200 import _lib
+    n = C.c_int()
+    _lib.load().phy_device_count(C.byref(n))
+    if n.value < 2:
+        pytest.skip("needs 2 GPUs")
+    script = tmp_path / "w.py"
+    script.write_text(WORKER)
+    out = tmp_path / "out.fa"
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, str(r), "2", str(tmp_path / "id"), str(keep), str(out)],
+                              stderr=subprocess.PIPE, text=True) for r in range(2)]
+    for p in procs:
+        _, e = p.communicate(timeout=300)
+        assert p.returncode == 0, e[-3000:]
+    assert out.read_text() == H.golden_filter_fa(keep)
