@@ -76,6 +76,13 @@ int phy_index_count(phy_ctx* ctx, int* n_resident);
 /* packed body bytes back to the host (tests, cache files) */
 int phy_index_download(phy_ctx* ctx, int idx_id, void* host_out, uint64_t nbytes);
 
+/* ------------------------------------------------------------- pinned host memory
+ * Optional: buffers from phy_host_alloc are page-locked, so phy_queries_set /
+ * phy_index_push DMA straight from them (no staging copy).  Any other host pointer
+ * works too (it is staged through the library's pinned ring). */
+int phy_host_alloc(size_t bytes, void** out);
+void phy_host_free(void* p);
+
 /* --------------------------------------------------------------------- queries
  * seq_concat: ASCII bases of all queries back to back (upper-case ACGT only,
  * the contract of intermediate/01_queries_merged, Snakefile:326-332);

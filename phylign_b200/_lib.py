@@ -82,7 +82,9 @@ PROTOTYPES = {
     "phy_index_info_get": (C.c_int, [_P, C.c_int, C.POINTER(IndexInfo)]),
     "phy_index_count": (C.c_int, [_P, C.POINTER(C.c_int)]),
     "phy_index_download": (C.c_int, [_P, C.c_int, C.c_void_p, C.c_uint64]),
-    "phy_queries_set": (C.c_int, [_P, C.c_char_p, C.c_void_p, C.c_uint32]),
+    "phy_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "phy_host_free": (None, [C.c_void_p]),
+    "phy_queries_set": (C.c_int, [_P, C.c_void_p, C.c_void_p, C.c_uint32]),
     "phy_match_run": (C.c_int, [_P, C.POINTER(MatchParams), C.c_uint32]),
     "phy_results_fetch": (C.c_int, [_P, C.POINTER(C.POINTER(Results))]),
     "phy_results_free": (None, [C.POINTER(Results)]),

@@ -116,7 +116,7 @@ extern "C" void phy_ctx_destroy(phy_ctx* ctx) {
                     ctx->d_qcount.p, ctx->d_scores.p, ctx->d_items.p, ctx->d_slotq.p, ctx->d_ckey.p, ctx->d_qoffs_c.p,
                     ctx->d_foffs.p, ctx->d_scan_tmp.p, ctx->d_cval.p, ctx->d_qcursor.p, ctx->d_nfinal.p,
                     ctx->d_final.p, ctx->d_flush.p, ctx->d_foffs_all.p, ctx->d_rank_base.p,
-                    ctx->d_recv.p};
+                    ctx->d_recv.p, ctx->d_units_sorted.p, ctx->d_unit_flag.p, ctx->d_unit_id.p, ctx->d_unit_pos.p};
     for (void* b : bufs) if (b) cudaFree(b);
     for (int i = 0; i < 2; i++) {
         if (ctx->pin[i]) cudaFreeHost(ctx->pin[i]);
@@ -130,10 +130,84 @@ extern "C" void phy_ctx_destroy(phy_ctx* ctx) {
     delete ctx;
 }
 
-// host (pageable) -> device through the pinned ring; src is free again on return
+// ---- process-wide pool of pinned host blocks (results, caller buffers) -------------------------
+// cudaHostAlloc/cudaFreeHost cost milliseconds; result buffers of consecutive steps have the
+// same size class, so freed blocks are kept and handed out again.
+#include <map>
+#include <mutex>
+static std::mutex g_pin_mu;
+static std::multimap<size_t, void*> g_pin_free;      // capacity -> block
+static std::map<void*, size_t> g_pin_cap;            // every live or cached block
+static size_t pin_class(size_t n) {
+    size_t c = 4096;
+    while (c < n) c <<= 1;
+    return c;
+}
+void* phy_pinned_alloc(size_t bytes) {
+    const size_t cap = pin_class(bytes ? bytes : 1);
+    {
+        std::lock_guard<std::mutex> lk(g_pin_mu);
+        auto it = g_pin_free.find(cap);
+        if (it != g_pin_free.end()) {
+            void* p = it->second;
+            g_pin_free.erase(it);
+            return p;
+        }
+    }
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, cap, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    g_pin_cap[p] = cap;
+    return p;
+}
+void phy_pinned_free(void* p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    auto it = g_pin_cap.find(p);
+    if (it == g_pin_cap.end()) return;
+    size_t cached = 0;
+    for (auto& kv : g_pin_free) cached += kv.first;
+    if (cached + it->second > (size_t(4) << 30)) {   // keep at most 4 GiB parked
+        cudaFreeHost(p);
+        g_pin_cap.erase(it);
+        return;
+    }
+    g_pin_free.insert({it->second, p});
+}
+static bool is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
+extern "C" int phy_host_alloc(size_t bytes, void** out) {
+    if (!out) return PHY_ERR_ARG;
+    *out = phy_pinned_alloc(bytes);
+    if (!*out) {
+        phy_set_error(nullptr, "cannot allocate %llu bytes of pinned host memory", (unsigned long long)bytes);
+        return PHY_ERR_NOMEM;
+    }
+    return PHY_OK;
+}
+extern "C" void phy_host_free(void* p) { phy_pinned_free(p); }
+
+// host -> device; src is free again on return.  Pinned sources (phy_host_alloc) are DMA'd
+// directly, pageable ones go through the pinned ring.
 int phy_h2d(phy_ctx* ctx, void* dst, const void* src, size_t bytes) {
     const uint8_t* s = (const uint8_t*)src;
     uint8_t* d = (uint8_t*)dst;
+    if (bytes >= (1u << 16) && is_pinned(src)) {
+        PHY_CUDA(ctx, cudaMemcpyAsync(d, s, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        PHY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->h2d_bytes += bytes;
+        return PHY_OK;
+    }
     while (bytes) {
         size_t n = std::min(bytes, ctx->pin_bytes);
         int slot = ctx->pin_cur;
@@ -152,6 +226,11 @@ int phy_h2d(phy_ctx* ctx, void* dst, const void* src, size_t bytes) {
 int phy_d2h(phy_ctx* ctx, void* dst, const void* src, size_t bytes) {
     uint8_t* d = (uint8_t*)dst;
     const uint8_t* s = (const uint8_t*)src;
+    if (bytes >= (1u << 16) && is_pinned(dst)) {
+        PHY_CUDA(ctx, cudaMemcpyAsync(d, s, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        PHY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return PHY_OK;
+    }
     // two slots in flight: copy chunk i+1 while chunk i is memcpy'd out
     size_t off = 0, pend_n[2] = {0, 0}, pend_off[2] = {0, 0};
     int slot = 0;
@@ -503,11 +582,11 @@ extern "C" int phy_results_fetch(phy_ctx* ctx, phy_results** out) {
     r->n_indexes = (uint32_t)n_idx;
     r->n_units = ctx->n_units;
     r->n_hits = ctx->n_hits;
-    r->units = (phy_unit*)malloc(std::max<uint64_t>(1, r->n_units) * sizeof(phy_unit));
-    r->hits = (phy_hit*)malloc(std::max<uint64_t>(1, r->n_hits) * sizeof(phy_hit));
+    r->units = (phy_unit*)phy_pinned_alloc(std::max<uint64_t>(1, r->n_units) * sizeof(phy_unit));
+    r->hits = (phy_hit*)phy_pinned_alloc(std::max<uint64_t>(1, r->n_hits) * sizeof(phy_hit));
     uint32_t* nk = (uint32_t*)malloc((size_t)(ctx->nq + 1) * sizeof(uint32_t));
     if (!r->units || !r->hits || !nk) {
-        free(r->units); free(r->hits); free(nk); free(r);
+        phy_pinned_free(r->units); phy_pinned_free(r->hits); free(nk); free(r);
         phy_set_error(ctx, "host memory exhausted");
         return PHY_ERR_NOMEM;
     }
@@ -520,9 +599,10 @@ extern "C" int phy_results_fetch(phy_ctx* ctx, phy_results** out) {
         phy_results_free(r);
         return rc;
     }
-    std::sort(r->units, r->units + r->n_units, [](const phy_unit& a, const phy_unit& b) {
-        return a.index != b.index ? a.index < b.index : a.query < b.query;
-    });
+    if (!ctx->units_ordered)  // the device orders them unless the (index, query) table was too large
+        std::sort(r->units, r->units + r->n_units, [](const phy_unit& a, const phy_unit& b) {
+            return a.index != b.index ? a.index < b.index : a.query < b.query;
+        });
     r->h2d_bytes = ctx->h2d_bytes;
     r->d2h_bytes = r->n_units * sizeof(phy_unit) + r->n_hits * sizeof(phy_hit);
     *out = r;
@@ -531,8 +611,8 @@ extern "C" int phy_results_fetch(phy_ctx* ctx, phy_results** out) {
 
 extern "C" void phy_results_free(phy_results* r) {
     if (!r) return;
-    free(r->units);
-    free(r->hits);
+    phy_pinned_free(r->units);
+    phy_pinned_free(r->hits);
     free((void*)r->n_kmers);
     free(r);
 }
@@ -572,8 +652,9 @@ extern "C" int phy_merged_fetch(phy_ctx* ctx, phy_merged** out) {
     m->n_queries = ctx->nq;
     const bool holder = ctx->n_ranks == 1 || ctx->rank == 0;
     const uint64_t n = holder ? ctx->n_final : 0;
-    m->offs = (uint64_t*)calloc((size_t)ctx->nq + 1, sizeof(uint64_t));
-    m->cands = (phy_cand*)malloc(std::max<uint64_t>(1, n) * sizeof(phy_cand));
+    m->offs = (uint64_t*)phy_pinned_alloc(((size_t)ctx->nq + 1) * sizeof(uint64_t));
+    m->cands = (phy_cand*)phy_pinned_alloc(std::max<uint64_t>(1, n) * sizeof(phy_cand));
+    if (m->offs) memset(m->offs, 0, ((size_t)ctx->nq + 1) * sizeof(uint64_t));
     if (!m->offs || !m->cands) {
         phy_merged_free(m);
         phy_set_error(ctx, "host memory exhausted");
@@ -623,8 +704,8 @@ extern "C" int phy_merge_host(phy_ctx* ctx, uint32_t n_queries, uint32_t top_n, 
 
 extern "C" void phy_merged_free(phy_merged* m) {
     if (!m) return;
-    free(m->offs);
-    free(m->cands);
+    phy_pinned_free(m->offs);
+    phy_pinned_free(m->cands);
     free(m);
 }
 

@@ -183,6 +183,9 @@ struct GatherArgs {
     uint64_t hits_cap;
     unsigned long long* counters;  // [0] hits cursor, [1] units cursor
     uint32_t* qcount;
+    uint32_t* unit_flag;  // [index slot][query] 0/1 (null: host orders the units)
+    uint32_t* unit_id;    // [index slot][query] position in units[]
+    uint32_t nq;
 };
 
 // Threshold (cobs counts_to_result), top-N + ties (postprocess_cobs.py:21-38) and emission of
@@ -237,6 +240,11 @@ __device__ __forceinline__ void select_and_emit(const uint32_t (&pl)[P][4], cons
             phy_unit pu;
             pu.query = q; pu.index = idx_id; pu.n_pass = n_pass; pu.n_kept = n_kept; pu.offset = off;
             a.units[u] = pu;
+            if (a.unit_flag) {
+                const uint64_t cell = (uint64_t)idx_id * a.nq + q;
+                a.unit_flag[cell] = 1u;
+                a.unit_id[cell] = (uint32_t)u;
+            }
         }
         atomicAdd(&a.qcount[q], n_kept);
     }
@@ -501,7 +509,7 @@ __global__ void __launch_bounds__(256) select_scores_kernel(
     const uint32_t* __restrict__ scores, uint32_t n_docs, const uint32_t* __restrict__ slotq,
     const uint32_t* __restrict__ Tq, const uint32_t* __restrict__ nk, uint32_t top_n,
     uint32_t idx_id, phy_unit* units, uint64_t units_cap, phy_hit* hits, uint64_t hits_cap,
-    unsigned long long* counters, uint32_t* qcount) {
+    unsigned long long* counters, uint32_t* qcount, uint32_t* unit_flag, uint32_t* unit_id, uint32_t nq) {
     __shared__ uint32_t sm[8];
     __shared__ uint32_t sm_scan[256];
     __shared__ unsigned long long sm_off;
@@ -540,6 +548,11 @@ __global__ void __launch_bounds__(256) select_scores_kernel(
             phy_unit pu;
             pu.query = q; pu.index = idx_id; pu.n_pass = n_pass; pu.n_kept = n_kept; pu.offset = off;
             units[u] = pu;
+            if (unit_flag) {
+                const uint64_t cell = (uint64_t)idx_id * nq + q;
+                unit_flag[cell] = 1u;
+                unit_id[cell] = (uint32_t)u;
+            }
         }
         atomicAdd(&qcount[q], n_kept);
         sm_off = off;
@@ -710,6 +723,18 @@ int phy_launch_gather(phy_ctx* ctx, const phy_match_params* p) {
         a.units = ctx->d_units.p; a.units_cap = ctx->d_units.cap;
         a.hits = ctx->d_hits.p; a.hits_cap = ctx->d_hits.cap;
         a.counters = ctx->d_counters.p; a.qcount = ctx->d_qcount.p;
+        // dense (index slot, query) table so the unit list can be put in (index, query) order on
+        // the device (deterministic output, no host sort); skipped when it would be huge
+        const uint64_t cells = (uint64_t)ctx->idx.size() * ctx->nq;
+        a.unit_flag = a.unit_id = nullptr;
+        a.nq = ctx->nq;
+        if (cells && cells <= (1ull << 27)) {
+            PHY_TRY(phy_ensure(ctx, ctx->d_unit_flag, cells + 1));
+            PHY_TRY(phy_ensure(ctx, ctx->d_unit_id, cells + 1));
+            PHY_CUDA(ctx, cudaMemsetAsync(ctx->d_unit_flag.p, 0, cells * sizeof(uint32_t), ctx->stream));
+            a.unit_flag = ctx->d_unit_flag.p;
+            a.unit_id = ctx->d_unit_id.p;
+        }
         if (!fastq.empty()) {
             for (int c = 0; c < 6; c++) {
                 if (cls[c].empty()) continue;
@@ -759,7 +784,7 @@ int phy_launch_gather(phy_ctx* ctx, const phy_match_params* p) {
                 select_scores_kernel<<<(unsigned)part.size(), 256, 0, ctx->stream>>>(
                     ctx->d_scores.p, ix.d.n_docs, ctx->d_slotq.p, ctx->d_T.p, ctx->d_nk.p, p->top_n,
                     ix.d.idx_id, ctx->d_units.p, ctx->d_units.cap, ctx->d_hits.p, ctx->d_hits.cap,
-                    ctx->d_counters.p, ctx->d_qcount.p);
+                    ctx->d_counters.p, ctx->d_qcount.p, a.unit_flag, a.unit_id, ctx->nq);
                 ctx->launches++;
                 PHY_CUDA(ctx, cudaGetLastError());
             }
@@ -770,6 +795,11 @@ int phy_launch_gather(phy_ctx* ctx, const phy_match_params* p) {
         if (cnt[0] <= ctx->d_hits.cap && cnt[1] <= ctx->d_units.cap) {
             ctx->n_hits = cnt[0];
             ctx->n_units = cnt[1];
+            ctx->units_ordered = false;
+            if (a.unit_flag && ctx->n_units) {
+                PHY_TRY(phy_order_units(ctx, cells));
+                ctx->units_ordered = true;
+            }
             return PHY_OK;
         }
         hits_cap = std::max<uint64_t>(cnt[0], hits_cap);

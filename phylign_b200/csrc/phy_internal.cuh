@@ -84,7 +84,10 @@ struct phy_ctx {
 
     // match outputs (device resident until fetched)
     bool have_match = false, have_merged = false;
-    DevBuf<phy_unit> d_units;
+    DevBuf<phy_unit> d_units, d_units_sorted;
+    DevBuf<uint32_t> d_unit_flag, d_unit_id;
+    DevBuf<uint64_t> d_unit_pos;
+    bool units_ordered = false;
     DevBuf<phy_hit> d_hits;
     DevBuf<unsigned long long> d_counters;  // [0] n_hits [1] n_units [2] error info
     DevBuf<uint32_t> d_qcount;              // kept hits per query (merge sizing)
@@ -164,6 +167,7 @@ int phy_nccl_merge(phy_ctx* ctx, uint32_t top_n);
 int phy_merge_segments(phy_ctx* ctx, uint32_t top_n);
 int phy_exscan(phy_ctx* ctx, const uint32_t* d_in, uint64_t n, uint64_t* d_out, uint64_t* total_host);
 int phy_lpr_for_stride(uint32_t stride);
+int phy_order_units(phy_ctx* ctx, uint64_t cells);
 int phy_restride_chunk(phy_ctx* ctx, HostIndex& ix, const uint8_t* d_src, uint64_t body_off,
                        uint64_t nbytes);
 int phy_destride(phy_ctx* ctx, const HostIndex& ix, uint8_t* d_dst);

@@ -217,6 +217,15 @@ __global__ void __launch_bounds__(256) compact_final_kernel(const uint64_t* __re
     }
 }
 
+// units[] -> (index, query) order: cell c of the dense table goes to position scan[c]
+__global__ void __launch_bounds__(256) order_units_kernel(const uint32_t* __restrict__ flag,
+                                                          const uint32_t* __restrict__ id,
+                                                          const uint64_t* __restrict__ pos, uint64_t cells,
+                                                          const phy_unit* __restrict__ in, phy_unit* __restrict__ out) {
+    for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < cells; c += (uint64_t)gridDim.x * blockDim.x)
+        if (flag[c]) out[pos[c]] = in[id[c]];
+}
+
 __global__ void __launch_bounds__(256) cands_to_keys_kernel(const phy_cand* __restrict__ c, uint64_t n,
                                                             uint64_t* __restrict__ ckey, uint32_t* __restrict__ cval) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -227,6 +236,31 @@ __global__ void __launch_bounds__(256) cands_to_keys_kernel(const phy_cand* __re
 }
 
 }  // namespace
+
+int phy_order_units(phy_ctx* ctx, uint64_t cells) {
+    PHY_TRY(phy_ensure(ctx, ctx->d_unit_pos, cells + 2));
+    uint64_t total = 0;
+    PHY_TRY(phy_exscan(ctx, ctx->d_unit_flag.p, cells, ctx->d_unit_pos.p, &total));
+    if (total != ctx->n_units) {
+        phy_set_error(ctx, "internal: unit table holds %llu entries, expected %llu", (unsigned long long)total,
+                      (unsigned long long)ctx->n_units);
+        return PHY_ERR_STATE;
+    }
+    if (ctx->d_units_sorted.cap != ctx->d_units.cap) {  // twin of d_units: exactly the same capacity (they swap)
+        phy_release(ctx, ctx->d_units_sorted);
+        void* p = nullptr;
+        PHY_TRY(phy_dev_alloc(ctx, &p, ctx->d_units.cap * sizeof(phy_unit), true));
+        ctx->d_units_sorted.p = (phy_unit*)p;
+        ctx->d_units_sorted.cap = ctx->d_units.cap;
+    }
+    unsigned blocks = (unsigned)std::min<uint64_t>((cells + 255) / 256, 148ull * 16);
+    order_units_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_unit_flag.p, ctx->d_unit_id.p, ctx->d_unit_pos.p, cells,
+                                                       ctx->d_units.p, ctx->d_units_sorted.p);
+    ctx->launches++;
+    PHY_CUDA(ctx, cudaGetLastError());
+    std::swap(ctx->d_units, ctx->d_units_sorted);
+    return PHY_OK;
+}
 
 // candidates supplied by the host, already grouped per query (offs[nq+1])
 int phy_merge_host_impl(phy_ctx* ctx, uint32_t nq, uint32_t top_n, const uint64_t* offs, const phy_cand* cands) {

@@ -31,13 +31,42 @@ class ResidentIndex:
         self.batch_rank = idx_id
 
 
-class MatchResult:
-    """Non-empty (query, index) blocks of one match call (numpy copies of phy_results)."""
+class _Owned:
+    """Keeps a library-owned result block alive; frees it when the last view holder dies."""
 
-    def __init__(self, units, hits, n_kmers, n_queries, h2d_bytes, d2h_bytes):
+    def __init__(self, ptr, free_fn):
+        self.ptr, self._free = ptr, free_fn
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self._free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+def _view(ptr, n, dtype, owner):
+    """Zero-copy numpy view of n records at a ctypes pointer (pinned, owned by `owner`)."""
+    if n == 0:
+        return np.zeros(0, dtype)
+    buf = (C.c_char * (n * dtype.itemsize)).from_address(C.addressof(ptr.contents))
+    a = np.frombuffer(buf, dtype=dtype)
+    a.flags.writeable = False
+    return a
+
+
+class MatchResult:
+    """Non-empty (query, index) blocks of one match call.
+
+    `units` / `hits` are zero-copy views of the library's pinned result buffers; they stay
+    valid as long as this object lives (copy them to keep them longer)."""
+
+    def __init__(self, units, hits, n_kmers, n_queries, h2d_bytes, d2h_bytes, owner=None):
         self.units, self.hits, self.n_kmers = units, hits, n_kmers
         self.n_queries = n_queries
         self.h2d_bytes, self.d2h_bytes = h2d_bytes, d2h_bytes
+        self._owner = owner
 
     def units_of(self, idx_id):
         lo = np.searchsorted(self.units["index"], idx_id, "left")
@@ -47,6 +76,30 @@ class MatchResult:
     def hits_of(self, unit):
         o = int(unit["offset"])
         return self.hits[o:o + int(unit["n_kept"])]
+
+
+class PinnedBuffer:
+    """Page-locked host buffer from phy_host_alloc, exposed as a numpy uint8 array."""
+
+    def __init__(self, nbytes: int):
+        self._L = _lib.load()
+        self._p = C.c_void_p()
+        _lib.check(self._L.phy_host_alloc(max(1, nbytes), C.byref(self._p)))
+        self.nbytes = nbytes
+        self.array = np.frombuffer((C.c_char * max(1, nbytes)).from_address(self._p.value), dtype=np.uint8)[:nbytes]
+
+    @property
+    def ptr(self):
+        return self._p.value
+
+    def __del__(self):
+        try:
+            if self._p:
+                self.array = None
+                self._L.phy_host_free(self._p)
+                self._p = C.c_void_p()
+        except Exception:
+            pass
 
 
 class Matcher:
@@ -178,10 +231,23 @@ class Matcher:
             offs[1:] = np.cumsum([len(s) for _, s in self.records], dtype=np.uint64)
         self.set_queries_raw(cat, offs)
 
-    def set_queries_raw(self, cat: bytes, offs: np.ndarray):
-        offs = np.ascontiguousarray(offs, dtype=np.uint64)
+    def set_queries_raw(self, cat, offs):
+        """cat: bytes / numpy uint8 array / PinnedBuffer with all bases; offs: uint64[nq+1]
+        (numpy array or PinnedBuffer).  Pinned inputs are DMA'd without a staging copy."""
+        def addr(x):
+            if isinstance(x, PinnedBuffer):
+                return x.ptr
+            if isinstance(x, np.ndarray):
+                return x.ctypes.data
+            return C.cast(C.c_char_p(x), C.c_void_p).value
+        if isinstance(offs, PinnedBuffer):
+            nq = offs.nbytes // 8 - 1
+        else:
+            offs = np.ascontiguousarray(offs, dtype=np.uint64)
+            nq = len(offs) - 1
         self._seq_keepalive = (cat, offs)
-        self._ck(self._L.phy_queries_set(self._ctx, cat, offs.ctypes.data, len(offs) - 1))
+        self._nq = nq
+        self._ck(self._L.phy_queries_set(self._ctx, addr(cat), addr(offs), nq))
 
     # ------------------------------------------------------------------ match
     def match_run(self, threshold: float, top_n: int = 0, floor_mode: bool = False, merge_top_n: int = 0):
@@ -191,37 +257,30 @@ class Matcher:
     def fetch(self) -> MatchResult:
         rp = C.POINTER(_lib.Results)()
         self._ck(self._L.phy_results_fetch(self._ctx, C.byref(rp)))
-        try:
-            r = rp.contents
-            nu, nh, nq = int(r.n_units), int(r.n_hits), int(r.n_queries)
-            units = np.frombuffer(C.string_at(r.units, nu * UNIT_DT.itemsize), dtype=UNIT_DT).copy() \
-                if nu else np.zeros(0, UNIT_DT)
-            hits = np.frombuffer(C.string_at(r.hits, nh * HIT_DT.itemsize), dtype=HIT_DT).copy() \
-                if nh else np.zeros(0, HIT_DT)
-            nk = np.frombuffer(C.string_at(r.n_kmers, nq * 4), dtype=np.uint32).copy() if nq else \
-                np.zeros(0, np.uint32)
-            return MatchResult(units, hits, nk, nq, int(r.h2d_bytes), int(r.d2h_bytes))
-        finally:
-            self._L.phy_results_free(rp)
+        owner = _Owned(rp, self._L.phy_results_free)
+        r = rp.contents
+        nu, nh, nq = int(r.n_units), int(r.n_hits), int(r.n_queries)
+        units = _view(r.units, nu, UNIT_DT, owner)
+        hits = _view(r.hits, nh, HIT_DT, owner)
+        nk = np.frombuffer(C.string_at(r.n_kmers, nq * 4), dtype=np.uint32) if nq else np.zeros(0, np.uint32)
+        return MatchResult(units, hits, nk, nq, int(r.h2d_bytes), int(r.d2h_bytes), owner)
 
     def match(self, threshold: float, top_n: int = 0, floor_mode: bool = False, merge_top_n: int = 0):
         self.match_run(threshold, top_n, floor_mode, merge_top_n)
         return self.fetch()
 
     def merged(self):
-        """(offs[nq+1], cands structured array) of the cross-index top-N + ties merge."""
+        """(offs[nq+1], cands structured array) of the cross-index top-N + ties merge.
+        Zero-copy views of pinned library memory, kept alive by the arrays' owner (`.base`)."""
         mp = C.POINTER(_lib.Merged)()
         self._ck(self._L.phy_merged_fetch(self._ctx, C.byref(mp)))
-        try:
-            m = mp.contents
-            nq = int(m.n_queries)
-            offs = np.frombuffer(C.string_at(m.offs, (nq + 1) * 8), dtype=np.uint64).copy()
-            n = int(offs[-1])
-            cands = np.frombuffer(C.string_at(m.cands, n * CAND_DT.itemsize), dtype=CAND_DT).copy() \
-                if n else np.zeros(0, CAND_DT)
-            return offs, cands
-        finally:
-            self._L.phy_merged_free(mp)
+        owner = _Owned(mp, self._L.phy_merged_free)
+        m = mp.contents
+        nq = int(m.n_queries)
+        offs = _view(m.offs, nq + 1, np.dtype("<u8"), owner)
+        cands = _view(m.cands, int(offs[-1]), CAND_DT, owner)
+        self._merged_owner = owner      # valid until the next merged() call
+        return offs, cands
 
     def merge_host(self, offs: np.ndarray, cands: np.ndarray, top_n: int):
         """filter_queries.py entry: merge host-supplied candidates (CAND_DT, grouped by query)."""
@@ -232,7 +291,7 @@ class Matcher:
         return self.merged()
 
     def scores(self, idx_id) -> np.ndarray:
-        nq = len(self._seq_keepalive[1]) - 1
+        nq = self._nq
         d = self.indexes[idx_id].header.n_docs
         out = np.zeros((nq, d), dtype=np.uint32)
         self._ck(self._L.phy_scores(self._ctx, idx_id, out.ctypes.data))
