@@ -306,7 +306,7 @@ def run_ours(args, w, rank, world, local_rank):
                                       "n_merged": int(len(mcands))}),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None,
-                         "kernel": "gather_count_bulk_kernel<32,3,4>",
+                         "kernel": "gather_count_ring_kernel<32,3,4>",
                          "note": f"algorithmic bytes of rank 0's shard per launch / mean CUDA-event duration of the "
                                  f"gather phase ({g_ms:.2f} ms, one launch per step); peak = {peak_src}"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

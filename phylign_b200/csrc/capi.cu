@@ -82,7 +82,7 @@ extern "C" int phy_ctx_create(phy_ctx** out, int device, uint64_t hbm_budget) {
     phy_ctx* ctx = new phy_ctx();
     ctx->device = device;
     ctx->n_sm = prop.multiProcessorCount;
-    ctx->force_v1 = getenv("PHY_FORCE_V1") && atoi(getenv("PHY_FORCE_V1")) != 0;
+    if (getenv("PHY_KERNEL_PATH")) ctx->kernel_path = atoi(getenv("PHY_KERNEL_PATH"));
     PHY_CUDA(ctx, cudaSetDevice(device));
     size_t fr = 0, tot = 0;
     PHY_CUDA(ctx, cudaMemGetInfo(&fr, &tot));
@@ -255,8 +255,15 @@ int phy_d2h(phy_ctx* ctx, void* dst, const void* src, size_t bytes) {
 }
 
 // ---- index store --------------------------------------------------------------------
+// Row stride in HBM: a power of two up to 128 B (a row then never straddles a 128-B line:
+// measured 17.8 ms vs 15.3 ms for 83-B rows at stride 96 vs 128, profiles/r01_sweep_docs_*),
+// a multiple of 32 B (the DRAM sector) above.
 static uint32_t stride_for(uint32_t row_size) {
-    if (row_size <= 32) return (row_size + 15u) / 16u * 16u;
+    if (row_size <= 128) {
+        uint32_t s = 16;
+        while (s < row_size) s <<= 1;
+        return s;
+    }
     return (row_size + 31u) / 32u * 32u;
 }
 

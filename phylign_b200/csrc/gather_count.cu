@@ -448,6 +448,184 @@ __global__ void __launch_bounds__(WARPS * 32) gather_count_bulk_kernel(const Gat
     }
 }
 
+// ---- Fused path C: lane-private cp.async ring (all strides, one hash function) --------------
+// Same ring idea as path B, but every lane copies exactly the 16 B it will read back
+// (cp.async.cg, SASS LDGSTS.BYPASS) and tracks completion with commit/wait groups: no
+// mbarrier, no cross-lane visibility to arrange, 3 instructions per row instead of the
+// 9-instruction UBLKCP issue loop (which makes path B ALU-bound below 256-B rows,
+// profiles/r01_gather_d1000_*).  The carry-save tree is three levels deep here: per 32 rows
+// and 32 documents 4x7 + 2 + 1 full adders and ONE ripple into planes 5.. (2.25 LOP3 per
+// row-word instead of 3.5).
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// add 8 rows (v) into the vertical counters; batch number j selects the tree level to close
+template <int P>
+__device__ __forceinline__ void csa_batch3(uint32_t (&pl)[P][4], const uint4 (&v)[8], uint32_t j,
+                                           uint32_t (&p8)[4], uint32_t (&p16)[4]) {
+    static_assert(P >= 6, "three-level tree needs at least 6 planes");
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+        auto W = [&](const uint4& x) -> uint32_t { return w == 0 ? x.x : (w == 1 ? x.y : (w == 2 ? x.z : x.w)); };
+        uint32_t twoA, twoB, fourA, fourB, eight;
+        csa(twoA, pl[0][w], pl[0][w], W(v[0]), W(v[1]));
+        csa(twoB, pl[0][w], pl[0][w], W(v[2]), W(v[3]));
+        csa(fourA, pl[1][w], pl[1][w], twoA, twoB);
+        csa(twoA, pl[0][w], pl[0][w], W(v[4]), W(v[5]));
+        csa(twoB, pl[0][w], pl[0][w], W(v[6]), W(v[7]));
+        csa(fourB, pl[1][w], pl[1][w], twoA, twoB);
+        csa(eight, pl[2][w], pl[2][w], fourA, fourB);
+        if ((j & 1u) == 0) {
+            p8[w] = eight;
+        } else {
+            uint32_t sixteen;
+            csa(sixteen, pl[3][w], pl[3][w], p8[w], eight);
+            if ((j & 2u) == 0) {
+                p16[w] = sixteen;
+            } else {
+                uint32_t carry;
+                csa(carry, pl[4][w], pl[4][w], p16[w], sixteen);
+#pragma unroll
+                for (int p = 5; p < P; p++) {
+                    uint32_t t = pl[p][w] & carry;
+                    pl[p][w] ^= carry;
+                    carry = t;
+                }
+            }
+        }
+    }
+}
+// fold the pending eights / sixteens of an unfinished group of 4 batches into the planes
+template <int P>
+__device__ __forceinline__ void csa_flush3(uint32_t (&pl)[P][4], uint32_t nb, const uint32_t (&p8)[4],
+                                           const uint32_t (&p16)[4]) {
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+        if (nb & 1u) {
+            uint32_t carry = p8[w];
+#pragma unroll
+            for (int p = 3; p < P; p++) { uint32_t t = pl[p][w] & carry; pl[p][w] ^= carry; carry = t; }
+        }
+        if (nb & 2u) {
+            uint32_t carry = p16[w];
+#pragma unroll
+            for (int p = 4; p < P; p++) { uint32_t t = pl[p][w] & carry; pl[p][w] ^= carry; carry = t; }
+        }
+    }
+}
+
+#ifndef PHY_RING_NB
+#define PHY_RING_NB 3
+#endif
+#ifndef PHY_RING_WARPS
+#define PHY_RING_WARPS 4
+#endif
+constexpr int RING_NB = PHY_RING_NB, RING_WARPS = PHY_RING_WARPS;
+
+template <int LPR, int NB, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) gather_count_ring_kernel(const GatherArgs a) {
+    constexpr int P = PHY_FUSED_PLANES;
+    constexpr int G = 32 / LPR;
+    constexpr int HB = LPR >= 8 ? LPR : 8;  // rows whose hashes are fetched per block
+    constexpr int NH = HB / LPR;            // hashes per lane per block
+    constexpr int BPH = HB / 8;             // batches per hash block
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int col = lane & (LPR - 1), g = lane / LPR, gbase = lane - col;
+    const unsigned gm = group_mask<LPR>(lane);
+    // lane-private slots: batch b, row r -> ring + b*4096 + r*512 + lane*16 (conflict-free LDS.128)
+    const uint32_t ring = smem_u32(smem) + wid * (NB * BULK_BATCH_BYTES) + lane * 16;
+    const uint64_t total = (uint64_t)a.n_class_idx * a.n_q;
+    const uint64_t n_wunits = (total + G - 1) / G;
+
+    for (;;) {
+        unsigned long long wu = 0;
+        if (lane == 0) wu = atomicAdd(&a.counters[3], 1ULL);
+        wu = __shfl_sync(FULL, wu, 0);
+        if (wu >= n_wunits) break;
+        const uint64_t gid = wu * G + g;
+        const bool live = gid < total;
+        uint32_t q = 0, nrows = 0, stride = 0, n_docs = 0, idx_id = 0;
+        uint64_t sig = 1, magic = 0;
+        const uint8_t* colbase = nullptr;
+        const uint64_t* hq = nullptr;
+        if (live) {
+            const uint32_t ipos = (uint32_t)(gid / a.n_q);
+            q = a.qlist[gid - (uint64_t)ipos * a.n_q];
+            const DevIndex& ix = a.indexes[a.class_idx[ipos]];
+            stride = ix.stride; n_docs = ix.n_docs; idx_id = ix.idx_id;
+            sig = ix.sig; magic = ix.magic;
+            colbase = ix.rows + col * 16;
+            nrows = a.nk[q];
+            hq = a.hashes + a.koffs[q];
+        }
+        uint32_t nmax = nrows;
+#pragma unroll
+        for (int o = 16; o >= LPR; o >>= 1) nmax = max(nmax, __shfl_xor_sync(FULL, nmax, o));
+        const uint32_t nb = (nmax + 7) >> 3;  // warp-uniform number of batches
+        const bool lane_on = (uint32_t)col * 16u < stride;
+
+        uint32_t pl[P][4], p8[4] = {0, 0, 0, 0}, p16[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int p = 0; p < P; p++) pl[p][0] = pl[p][1] = pl[p][2] = pl[p][3] = 0;
+
+        uint32_t myrow[NH];
+        uint64_t hnext[NH];
+#pragma unroll
+        for (int t = 0; t < NH; t++) {
+            myrow[t] = PHY_ROW_INVALID;
+            const uint32_t hidx = col + t * LPR;
+            hnext[t] = hidx < nrows ? __ldg(hq + hidx) : 0;
+        }
+        auto issue = [&](uint32_t j) {  // queue the 8 rows of batch j (all groups of the warp)
+            if (j < nb) {
+                const uint32_t hb = j / BPH, s = j % BPH;
+                if (s == 0) {
+#pragma unroll
+                    for (int t = 0; t < NH; t++) {
+                        const uint32_t hidx = hb * HB + col + t * LPR;
+                        myrow[t] = hidx < nrows ? phy_fastmod(hnext[t], sig, magic) : PHY_ROW_INVALID;
+                        const uint32_t hn = hidx + HB;
+                        hnext[t] = hn < nrows ? __ldg(hq + hn) : 0;
+                    }
+                }
+                const uint32_t dst = ring + (j % NB) * BULK_BATCH_BYTES;
+#pragma unroll
+                for (int r = 0; r < 8; r++) {
+                    const int src = LPR >= 8 ? gbase + (int)s * 8 + r : gbase + (r % LPR);
+                    const int slot = LPR >= 8 ? 0 : r / LPR;
+                    const uint32_t rr = __shfl_sync(FULL, myrow[slot], src);
+                    if (rr != PHY_ROW_INVALID && lane_on) cp_async16(dst + r * 512, colbase + (uint64_t)rr * stride);
+                }
+            }
+            cp_async_commit();  // (possibly empty) group: keeps the wait_group distance constant
+        };
+#pragma unroll 1
+        for (uint32_t j = 0; j < (uint32_t)NB; j++) issue(j);
+#pragma unroll 1
+        for (uint32_t j = 0; j < nb; j++) {
+            cp_async_wait<NB - 1>();  // batch j has landed (this lane's own 16-B pieces)
+            const uint32_t src = ring + (j % NB) * BULK_BATCH_BYTES;
+            uint4 v[8];
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                if (j * 8 + r < nrows && lane_on) v[r] = lds128(src + r * 512);
+                else v[r] = make_uint4(0, 0, 0, 0);
+            }
+            csa_batch3<P>(pl, v, j, p8, p16);
+            issue(j + NB);  // refill the slot: its values were consumed above by this very lane
+        }
+        cp_async_wait<0>();
+        csa_flush3<P>(pl, nb, p8, p16);
+        if (live) select_and_emit<LPR, P>(pl, a, q, idx_id, n_docs, nrows, lane, gm);
+        __syncwarp();
+    }
+}
+
 // General path: k-mers [k0,k1) of a query against ONE index and one 512-B column chunk,
 // flushed into a dense uint32 score row.  Used for queries with K > PHY_FUSED_KMAX, for
 // rows wider than 512 B (D > 4096) and by phy_scores().
@@ -602,6 +780,25 @@ int launch_bulk(const GatherArgs& a, cudaStream_t st, int n_sm) {
     return 0;
 }
 
+template <int LPR, int NB, int WARPS>
+int launch_ring(const GatherArgs& a, cudaStream_t st, int n_sm) {
+    constexpr int SMEM = WARPS * NB * BULK_BATCH_BYTES;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(gather_count_ring_kernel<LPR, NB, WARPS>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) return -1;
+        configured = true;
+    }
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gather_count_ring_kernel<LPR, NB, WARPS>,
+                                                      WARPS * 32, SMEM) != cudaSuccess || per_sm < 1) return -1;
+    constexpr int G = 32 / LPR;
+    uint64_t wunits = ((uint64_t)a.n_class_idx * a.n_q + G - 1) / G;
+    uint64_t blocks = std::min<uint64_t>((wunits + WARPS - 1) / WARPS, (uint64_t)n_sm * per_sm);
+    if (blocks) gather_count_ring_kernel<LPR, NB, WARPS><<<(unsigned)blocks, WARPS * 32, SMEM, st>>>(a);
+    return 0;
+}
+
 template <int LPR>
 void launch_accum(const DevIndex* ixp, const SlowItem* items, uint32_t n_items, uint32_t n_chunks,
                   const uint64_t* koffs, const uint64_t* hashes, uint64_t total_kmers,
@@ -742,7 +939,28 @@ int phy_launch_gather(phy_ctx* ctx, const phy_match_params* p) {
                 a.n_class_idx = (uint32_t)cls[c].size();
                 bool multi_hash = false;
                 for (uint32_t i : cls[c]) multi_hash |= ctx->idx[i].d.num_hashes > 1;
-                const bool bulk = c >= 3 && !multi_hash && !ctx->force_v1;
+                const bool ring = !multi_hash && ctx->kernel_path == 3;
+                if (ring) {  // path C: lane-private cp.async ring, persistent warps
+                    PHY_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p + 3, 0, sizeof(unsigned long long), ctx->stream));
+                    int rc = -1;
+                    switch (c) {
+                        case 0: rc = launch_ring<1, RING_NB, RING_WARPS>(a, ctx->stream, ctx->n_sm); break;
+                        case 1: rc = launch_ring<2, RING_NB, RING_WARPS>(a, ctx->stream, ctx->n_sm); break;
+                        case 2: rc = launch_ring<4, RING_NB, RING_WARPS>(a, ctx->stream, ctx->n_sm); break;
+                        case 3: rc = launch_ring<8, RING_NB, RING_WARPS>(a, ctx->stream, ctx->n_sm); break;
+                        case 4: rc = launch_ring<16, RING_NB, RING_WARPS>(a, ctx->stream, ctx->n_sm); break;
+                        default: rc = launch_ring<32, RING_NB, RING_WARPS>(a, ctx->stream, ctx->n_sm); break;
+                    }
+                    if (rc != 0) {
+                        phy_set_error(ctx, "cannot configure the ring gather kernel: %s",
+                                      cudaGetErrorString(cudaGetLastError()));
+                        return PHY_ERR_CUDA;
+                    }
+                    ctx->launches++;
+                    PHY_CUDA(ctx, cudaGetLastError());
+                    continue;
+                }
+                const bool bulk = c >= 3 && !multi_hash && ctx->kernel_path == 2;
                 if (bulk) {  // persistent warps pull units from counters[3]
                     PHY_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p + 3, 0, sizeof(unsigned long long), ctx->stream));
                     int rc = c == 3 ? launch_bulk<8, BULK_NB, BULK_WARPS>(a, ctx->stream, ctx->n_sm)

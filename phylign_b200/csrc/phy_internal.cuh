@@ -55,7 +55,7 @@ struct HostIndex {
 
 struct phy_ctx {
     int device = 0, n_sm = 148;
-    bool force_v1 = false;  // PHY_FORCE_V1=1: use the register-staged kernel everywhere (A/B runs)
+    int kernel_path = 3;  // PHY_KERNEL_PATH: 1 = register-staged (A), 2 = bulk-copy ring (B), 3 = cp.async ring (C)
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_ph[4] = {nullptr, nullptr, nullptr, nullptr};
     uint64_t budget = 0, used = 0;

@@ -14,7 +14,12 @@ from dataclasses import dataclass, field
 def row_stride(n_docs: int) -> int:
     """HBM bytes per row (must match stride_for() in csrc/capi.cu)."""
     rs = (n_docs + 7) // 8
-    return (rs + 15) // 16 * 16 if rs <= 32 else (rs + 31) // 32 * 32
+    if rs <= 128:
+        s = 16
+        while s < rs:
+            s <<= 1
+        return s
+    return (rs + 31) // 32 * 32
 
 
 @dataclass

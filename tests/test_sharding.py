@@ -58,7 +58,7 @@ def test_capped_budget_streams_overflow_rounds():
 
 
 def test_stride_rule_matches_library():
-    for docs, want in ((1, 16), (128, 16), (129, 32), (200, 32), (257, 64), (664, 96), (4000, 512),
+    for docs, want in ((1, 16), (128, 16), (129, 32), (200, 32), (257, 64), (664, 128), (520, 128), (4000, 512),
                        (4097, 544)):
         assert sharding.row_stride(docs) == want
 
