@@ -264,7 +264,7 @@ def run_ours(args, w, rank, world, local_rank):
     value = w["bases"] / (ms_per_step * 1e-3)
 
     # ---- end to end through the public API: host buffers in, host results out, every step
-    for _ in range(1):
+    for _ in range(max(2, args.warmup)):   # warm-up: the pinned result pool reaches its steady state after 2 passes
         m.set_queries_raw(pin_raw, pin_offs); m.match_run(THRESHOLD, TOP_N, merge_top_n=TOP_N); m.fetch(); m.merged()
     m.sync()
     barrier()
@@ -293,6 +293,14 @@ def run_ours(args, w, rank, world, local_rank):
         m.close()
         return
     peak, peak_src = measured_peak()
+    kernel = "gather_count_ring_kernel<32,3,4>"
+    traffic = None
+    try:   # DRAM bytes per launch from the committed ncu capture of this exact workload, else null
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        key = f"{kernel}|{w['n_reads']}|{w['read_len']}|{w['n_indexes']}|{w['n_docs']}|{world}"
+        traffic = tj[key]["traffic_bytes"] if key in tj else None
+    except Exception:
+        pass
     g_ms = float(np.mean(gather_ms))
     achieved = local_alg_bytes / (g_ms * 1e-3) / 1e9
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -305,8 +313,8 @@ def run_ours(args, w, rank, world, local_rank):
                                       "n_units": int(len(res.units)), "n_hits": int(len(res.hits)),
                                       "n_merged": int(len(mcands))}),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None,
-                         "kernel": "gather_count_ring_kernel<32,3,4>",
+                         "frac": achieved / peak, "traffic": traffic,
+                         "kernel": kernel,
                          "note": f"algorithmic bytes of rank 0's shard per launch / mean CUDA-event duration of the "
                                  f"gather phase ({g_ms:.2f} ms, one launch per step); peak = {peak_src}"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

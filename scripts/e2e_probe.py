@@ -1,0 +1,28 @@
+#!/usr/bin/env python3
+"""Per-iteration timing of the host<->device legs of one step (run on the GPU box)."""
+import sys, time, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import bench
+from phylign_b200 import _lib
+from phylign_b200.matcher import Matcher, PinnedBuffer
+
+n_idx = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+args = bench.argparse.Namespace(indexes=n_idx, docs=4000, genome_len=1_000_000, reads=100_000, read_len=1000)
+w = bench.workload(args)
+m = Matcher(0)
+specs = [_lib.SynthSpec(**bench.spec_kwargs(i, w)) for i in range(n_idx)]
+for i in range(n_idx):
+    m.add_synth_index(bench.batch_name(i), specs[i], w["signature_size"])
+m.set_ranks([bench.batch_name(i) for i in range(n_idx)])
+raw = m.synth_reads(specs, 3, 0, w["n_reads"], 1000, 51, 655)
+offs = np.arange(w["n_reads"] + 1, dtype=np.uint64) * 1000
+pr, po = PinnedBuffer(len(raw)), PinnedBuffer(offs.nbytes)
+pr.array[:] = np.frombuffer(raw, dtype=np.uint8); po.array[:] = offs.view(np.uint8)
+for it in range(8):
+    t = [time.perf_counter()]
+    m.set_queries_raw(pr, po); t.append(time.perf_counter())
+    m.match_run(0.7, 100, merge_top_n=100); t.append(time.perf_counter())
+    res = m.fetch(); t.append(time.perf_counter())
+    mo, mc = m.merged(); t.append(time.perf_counter())
+    print(it, [round((b - a) * 1e3, 2) for a, b in zip(t, t[1:])], len(res.units), len(res.hits), len(mc), flush=True)
