@@ -178,6 +178,9 @@ typedef struct phy_synth_spec {
 } phy_synth_spec;
 /* index must have been phy_index_begin()'d; fills and commits it */
 int phy_index_synth(phy_ctx* ctx, int idx_id, const phy_synth_spec* spec);
+/* `cobs classic-construct` step for real sequences: OR every k-mer of query q (queries set
+ * last) into document doc_of_query[q] of a committed index (0xFFFFFFFF = skip the query). */
+int phy_index_insert(phy_ctx* ctx, int idx_id, const uint32_t* doc_of_query);
 /* n_reads reads of read_len bases into host_out (n_reads*read_len ASCII bytes) */
 int phy_synth_reads(phy_ctx* ctx, const phy_synth_spec* specs, uint32_t n_specs,
                     uint64_t reads_seed, uint64_t first_read, uint32_t n_reads,

@@ -101,6 +101,7 @@ PROTOTYPES = {
     "phy_last_phase_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "phy_flush_l2": (C.c_int, [_P]),
     "phy_index_synth": (C.c_int, [_P, C.c_int, C.POINTER(SynthSpec)]),
+    "phy_index_insert": (C.c_int, [_P, C.c_int, C.c_void_p]),
     "phy_synth_reads": (C.c_int, [_P, C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32,
                                   C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]),
 }

@@ -772,6 +772,25 @@ extern "C" int phy_index_synth(phy_ctx* ctx, int idx_id, const phy_synth_spec* s
     return PHY_OK;
 }
 
+int phy_insert_kmers(phy_ctx* ctx, HostIndex& ix, const uint32_t* d_doc_of_query);
+
+extern "C" int phy_index_insert(phy_ctx* ctx, int idx_id, const uint32_t* doc_of_query) {
+    HostIndex* ix = get_index(ctx, idx_id);
+    if (!ix || !doc_of_query) return PHY_ERR_ARG;
+    if (!ix->committed || !ctx->have_queries) {
+        phy_set_error(ctx, "phy_index_insert needs a committed index and phy_queries_set");
+        return PHY_ERR_STATE;
+    }
+    PHY_CUDA(ctx, cudaSetDevice(ctx->device));
+    PHY_TRY(prepare_hashes(ctx, ix->term_size, ix->canon, ix->d.num_hashes));
+    PHY_TRY(phy_ensure(ctx, ctx->d_slotq, ctx->nq + 1));
+    PHY_TRY(phy_h2d(ctx, ctx->d_slotq.p, doc_of_query, (size_t)ctx->nq * sizeof(uint32_t)));
+    PHY_TRY(phy_insert_kmers(ctx, *ix, ctx->d_slotq.p));
+    PHY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->have_match = ctx->have_merged = false;
+    return PHY_OK;
+}
+
 extern "C" int phy_synth_reads(phy_ctx* ctx, const phy_synth_spec* specs, uint32_t n_specs, uint64_t reads_seed,
                                uint64_t first_read, uint32_t n_reads, uint32_t read_len, uint32_t random_q8,
                                uint32_t err_q16, char* host_out) {

@@ -526,16 +526,75 @@ __device__ __forceinline__ void csa_flush3(uint32_t (&pl)[P][4], uint32_t nb, co
 #endif
 constexpr int RING_NB = PHY_RING_NB, RING_WARPS = PHY_RING_WARPS;
 
-template <int LPR, int NB, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) gather_count_ring_kernel(const GatherArgs a) {
-    constexpr int P = PHY_FUSED_PLANES;
-    constexpr int G = 32 / LPR;
+// One unit per group of LPR lanes: add the rows of its `nrows` k-mers (hashes at hq) into pl.
+// `nmax` = largest nrows among the groups of the warp (all lanes run the same trip count).
+template <int LPR, int P, int NB>
+__device__ __forceinline__ void ring_accumulate(uint32_t (&pl)[P][4], uint32_t ring, const uint8_t* colbase,
+                                                bool lane_on, uint32_t stride, uint64_t sig, uint64_t magic,
+                                                const uint64_t* __restrict__ hq, uint32_t nrows, uint32_t nmax,
+                                                int lane) {
     constexpr int HB = LPR >= 8 ? LPR : 8;  // rows whose hashes are fetched per block
     constexpr int NH = HB / LPR;            // hashes per lane per block
     constexpr int BPH = HB / 8;             // batches per hash block
+    const int col = lane & (LPR - 1), gbase = lane - col;
+    const uint32_t nb = (nmax + 7) >> 3;    // warp-uniform number of batches
+    uint32_t p8[4] = {0, 0, 0, 0}, p16[4] = {0, 0, 0, 0};
+    uint32_t myrow[NH];
+    uint64_t hnext[NH];
+#pragma unroll
+    for (int t = 0; t < NH; t++) {
+        myrow[t] = PHY_ROW_INVALID;
+        const uint32_t hidx = col + t * LPR;
+        hnext[t] = hidx < nrows ? __ldg(hq + hidx) : 0;
+    }
+    auto issue = [&](uint32_t j) {  // queue the 8 rows of batch j (all groups of the warp)
+        if (j < nb) {
+            const uint32_t hb = j / BPH, s = j % BPH;
+            if (s == 0) {
+#pragma unroll
+                for (int t = 0; t < NH; t++) {
+                    const uint32_t hidx = hb * HB + col + t * LPR;
+                    myrow[t] = hidx < nrows ? phy_fastmod(hnext[t], sig, magic) : PHY_ROW_INVALID;
+                    const uint32_t hn = hidx + HB;
+                    hnext[t] = hn < nrows ? __ldg(hq + hn) : 0;
+                }
+            }
+            const uint32_t dst = ring + (j % NB) * BULK_BATCH_BYTES;
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                const int src = LPR >= 8 ? gbase + (int)s * 8 + r : gbase + (r % LPR);
+                const int slot = LPR >= 8 ? 0 : r / LPR;
+                const uint32_t rr = __shfl_sync(FULL, myrow[slot], src);
+                if (rr != PHY_ROW_INVALID && lane_on) cp_async16(dst + r * 512, colbase + (uint64_t)rr * stride);
+            }
+        }
+        cp_async_commit();  // (possibly empty) group: keeps the wait_group distance constant
+    };
+#pragma unroll 1
+    for (uint32_t j = 0; j < (uint32_t)NB; j++) issue(j);
+#pragma unroll 1
+    for (uint32_t j = 0; j < nb; j++) {
+        cp_async_wait<NB - 1>();  // batch j has landed (this lane's own 16-B pieces)
+        const uint32_t src = ring + (j % NB) * BULK_BATCH_BYTES;
+        uint4 v[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            if (j * 8 + r < nrows && lane_on) v[r] = lds128(src + r * 512);
+            else v[r] = make_uint4(0, 0, 0, 0);
+        }
+        csa_batch3<P>(pl, v, j, p8, p16);
+        issue(j + NB);  // refill the slot: its values were consumed above by this very lane
+    }
+    cp_async_wait<0>();
+    csa_flush3<P>(pl, nb, p8, p16);
+}
+
+template <int LPR, int P, int NB, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) gather_count_ring_kernel(const GatherArgs a) {
+    constexpr int G = 32 / LPR;
     extern __shared__ __align__(128) uint8_t smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int col = lane & (LPR - 1), g = lane / LPR, gbase = lane - col;
+    const int col = lane & (LPR - 1), g = lane / LPR;
     const unsigned gm = group_mask<LPR>(lane);
     // lane-private slots: batch b, row r -> ring + b*4096 + r*512 + lane*16 (conflict-free LDS.128)
     const uint32_t ring = smem_u32(smem) + wid * (NB * BULK_BATCH_BYTES) + lane * 16;
@@ -566,62 +625,74 @@ __global__ void __launch_bounds__(WARPS * 32) gather_count_ring_kernel(const Gat
         uint32_t nmax = nrows;
 #pragma unroll
         for (int o = 16; o >= LPR; o >>= 1) nmax = max(nmax, __shfl_xor_sync(FULL, nmax, o));
-        const uint32_t nb = (nmax + 7) >> 3;  // warp-uniform number of batches
-        const bool lane_on = (uint32_t)col * 16u < stride;
 
-        uint32_t pl[P][4], p8[4] = {0, 0, 0, 0}, p16[4] = {0, 0, 0, 0};
+        uint32_t pl[P][4];
 #pragma unroll
         for (int p = 0; p < P; p++) pl[p][0] = pl[p][1] = pl[p][2] = pl[p][3] = 0;
-
-        uint32_t myrow[NH];
-        uint64_t hnext[NH];
-#pragma unroll
-        for (int t = 0; t < NH; t++) {
-            myrow[t] = PHY_ROW_INVALID;
-            const uint32_t hidx = col + t * LPR;
-            hnext[t] = hidx < nrows ? __ldg(hq + hidx) : 0;
-        }
-        auto issue = [&](uint32_t j) {  // queue the 8 rows of batch j (all groups of the warp)
-            if (j < nb) {
-                const uint32_t hb = j / BPH, s = j % BPH;
-                if (s == 0) {
-#pragma unroll
-                    for (int t = 0; t < NH; t++) {
-                        const uint32_t hidx = hb * HB + col + t * LPR;
-                        myrow[t] = hidx < nrows ? phy_fastmod(hnext[t], sig, magic) : PHY_ROW_INVALID;
-                        const uint32_t hn = hidx + HB;
-                        hnext[t] = hn < nrows ? __ldg(hq + hn) : 0;
-                    }
-                }
-                const uint32_t dst = ring + (j % NB) * BULK_BATCH_BYTES;
-#pragma unroll
-                for (int r = 0; r < 8; r++) {
-                    const int src = LPR >= 8 ? gbase + (int)s * 8 + r : gbase + (r % LPR);
-                    const int slot = LPR >= 8 ? 0 : r / LPR;
-                    const uint32_t rr = __shfl_sync(FULL, myrow[slot], src);
-                    if (rr != PHY_ROW_INVALID && lane_on) cp_async16(dst + r * 512, colbase + (uint64_t)rr * stride);
-                }
-            }
-            cp_async_commit();  // (possibly empty) group: keeps the wait_group distance constant
-        };
-#pragma unroll 1
-        for (uint32_t j = 0; j < (uint32_t)NB; j++) issue(j);
-#pragma unroll 1
-        for (uint32_t j = 0; j < nb; j++) {
-            cp_async_wait<NB - 1>();  // batch j has landed (this lane's own 16-B pieces)
-            const uint32_t src = ring + (j % NB) * BULK_BATCH_BYTES;
-            uint4 v[8];
-#pragma unroll
-            for (int r = 0; r < 8; r++) {
-                if (j * 8 + r < nrows && lane_on) v[r] = lds128(src + r * 512);
-                else v[r] = make_uint4(0, 0, 0, 0);
-            }
-            csa_batch3<P>(pl, v, j, p8, p16);
-            issue(j + NB);  // refill the slot: its values were consumed above by this very lane
-        }
-        cp_async_wait<0>();
-        csa_flush3<P>(pl, nb, p8, p16);
+        ring_accumulate<LPR, P, NB>(pl, ring, colbase, (uint32_t)col * 16u < stride, stride, sig, magic, hq, nrows,
+                                    nmax, lane);
         if (live) select_and_emit<LPR, P>(pl, a, q, idx_id, n_docs, nrows, lane, gm);
+        __syncwarp();
+    }
+}
+
+// General path on the ring (one hash function): k-mers [k0,k1) of a query against ONE index and
+// one 512-B column chunk, flushed into a dense uint32 score row with atomics.  Chunks hold up
+// to 2^14-1 k-mers (14 planes).  For K > PHY_LONG_KMAX, rows wider than 512 B (D > 4096), phy_scores().
+constexpr int PHY_GENERAL_PLANES = 14;
+template <int LPR, int NB, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) accum_scores_ring_kernel(
+    const DevIndex* __restrict__ ixp, const SlowItem* __restrict__ items, uint32_t n_items, uint32_t n_chunks,
+    const uint64_t* __restrict__ koffs, const uint64_t* __restrict__ hashes, uint32_t* __restrict__ scores,
+    unsigned long long* __restrict__ counter) {
+    constexpr int P = PHY_GENERAL_PLANES;
+    constexpr int G = 32 / LPR;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int col = lane & (LPR - 1), g = lane / LPR;
+    const uint32_t ring = smem_u32(smem) + wid * (NB * BULK_BATCH_BYTES) + lane * 16;
+    const uint64_t total = (uint64_t)n_items * n_chunks;
+    const uint64_t n_wunits = (total + G - 1) / G;
+    const DevIndex& ix = *ixp;
+    const uint32_t stride = ix.stride, n_docs = ix.n_docs;
+    for (;;) {
+        unsigned long long wu = 0;
+        if (lane == 0) wu = atomicAdd(counter, 1ULL);
+        wu = __shfl_sync(FULL, wu, 0);
+        if (wu >= n_wunits) break;
+        const uint64_t gid = wu * G + g;
+        const bool live = gid < total;
+        SlowItem it = {0, 0, 0, 0};
+        uint32_t chunk = 0;
+        if (live) {
+            it = items[gid / n_chunks];
+            chunk = (uint32_t)(gid % n_chunks);
+        }
+        const uint32_t nrows = it.k1 - it.k0;
+        uint32_t nmax = nrows;
+#pragma unroll
+        for (int o = 16; o >= LPR; o >>= 1) nmax = max(nmax, __shfl_xor_sync(FULL, nmax, o));
+        const uint32_t byte0 = chunk * PHY_CHUNK_BYTES + (uint32_t)col * 16u;
+        uint32_t pl[P][4];
+#pragma unroll
+        for (int p = 0; p < P; p++) pl[p][0] = pl[p][1] = pl[p][2] = pl[p][3] = 0;
+        ring_accumulate<LPR, P, NB>(pl, ring, ix.rows + byte0, live && byte0 < stride, stride, ix.sig, ix.magic,
+                                    hashes + (live ? koffs[it.query] + it.k0 : 0), nrows, nmax, lane);
+        if (live) {
+            uint32_t* row = scores + (uint64_t)it.slot * n_docs;
+#pragma unroll
+            for (int w = 0; w < 4; w++) {
+                uint32_t any = 0;
+#pragma unroll
+                for (int p = 0; p < P; p++) any |= pl[p][w];
+                const uint32_t d0 = byte0 * 8u + w * 32u;
+                while (any) {
+                    int b = __ffs(any) - 1;
+                    any &= any - 1;
+                    if (d0 + b < n_docs) atomicAdd(&row[d0 + b], extract_score<P>(pl, w, b));
+                }
+            }
+        }
         __syncwarp();
     }
 }
@@ -780,23 +851,70 @@ int launch_bulk(const GatherArgs& a, cudaStream_t st, int n_sm) {
     return 0;
 }
 
-template <int LPR, int NB, int WARPS>
+template <int LPR, int P, int NB, int WARPS>
 int launch_ring(const GatherArgs& a, cudaStream_t st, int n_sm) {
     constexpr int SMEM = WARPS * NB * BULK_BATCH_BYTES;
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(gather_count_ring_kernel<LPR, NB, WARPS>,
+        if (cudaFuncSetAttribute(gather_count_ring_kernel<LPR, P, NB, WARPS>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) return -1;
         configured = true;
     }
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gather_count_ring_kernel<LPR, NB, WARPS>,
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gather_count_ring_kernel<LPR, P, NB, WARPS>,
                                                       WARPS * 32, SMEM) != cudaSuccess || per_sm < 1) return -1;
     constexpr int G = 32 / LPR;
     uint64_t wunits = ((uint64_t)a.n_class_idx * a.n_q + G - 1) / G;
     uint64_t blocks = std::min<uint64_t>((wunits + WARPS - 1) / WARPS, (uint64_t)n_sm * per_sm);
-    if (blocks) gather_count_ring_kernel<LPR, NB, WARPS><<<(unsigned)blocks, WARPS * 32, SMEM, st>>>(a);
+    if (blocks) gather_count_ring_kernel<LPR, P, NB, WARPS><<<(unsigned)blocks, WARPS * 32, SMEM, st>>>(a);
     return 0;
+}
+template <int P>
+int dispatch_ring(int c, const GatherArgs& a, cudaStream_t st, int n_sm) {
+    switch (c) {
+        case 0: return launch_ring<1, P, RING_NB, RING_WARPS>(a, st, n_sm);
+        case 1: return launch_ring<2, P, RING_NB, RING_WARPS>(a, st, n_sm);
+        case 2: return launch_ring<4, P, RING_NB, RING_WARPS>(a, st, n_sm);
+        case 3: return launch_ring<8, P, RING_NB, RING_WARPS>(a, st, n_sm);
+        case 4: return launch_ring<16, P, RING_NB, RING_WARPS>(a, st, n_sm);
+        default: return launch_ring<32, P, RING_NB, RING_WARPS>(a, st, n_sm);
+    }
+}
+
+template <int LPR>
+int launch_accum_ring(const DevIndex* ixp, const SlowItem* items, uint32_t n_items, uint32_t n_chunks,
+                      const uint64_t* koffs, const uint64_t* hashes, uint32_t* scores,
+                      unsigned long long* counter, cudaStream_t st, int n_sm) {
+    constexpr int NB = RING_NB, WARPS = RING_WARPS;
+    constexpr int SMEM = WARPS * NB * BULK_BATCH_BYTES;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(accum_scores_ring_kernel<LPR, NB, WARPS>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) return -1;
+        configured = true;
+    }
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, accum_scores_ring_kernel<LPR, NB, WARPS>, WARPS * 32,
+                                                      SMEM) != cudaSuccess || per_sm < 1) return -1;
+    constexpr int G = 32 / LPR;
+    uint64_t wunits = ((uint64_t)n_items * n_chunks + G - 1) / G;
+    uint64_t blocks = std::min<uint64_t>((wunits + WARPS - 1) / WARPS, (uint64_t)n_sm * per_sm);
+    if (blocks)
+        accum_scores_ring_kernel<LPR, NB, WARPS><<<(unsigned)blocks, WARPS * 32, SMEM, st>>>(
+            ixp, items, n_items, n_chunks, koffs, hashes, scores, counter);
+    return 0;
+}
+int dispatch_accum_ring(int lpr, const DevIndex* ixp, const SlowItem* items, uint32_t n_items, uint32_t n_chunks,
+                        const uint64_t* koffs, const uint64_t* hashes, uint32_t* scores,
+                        unsigned long long* counter, cudaStream_t st, int n_sm) {
+    switch (lpr) {
+        case 1: return launch_accum_ring<1>(ixp, items, n_items, n_chunks, koffs, hashes, scores, counter, st, n_sm);
+        case 2: return launch_accum_ring<2>(ixp, items, n_items, n_chunks, koffs, hashes, scores, counter, st, n_sm);
+        case 4: return launch_accum_ring<4>(ixp, items, n_items, n_chunks, koffs, hashes, scores, counter, st, n_sm);
+        case 8: return launch_accum_ring<8>(ixp, items, n_items, n_chunks, koffs, hashes, scores, counter, st, n_sm);
+        case 16: return launch_accum_ring<16>(ixp, items, n_items, n_chunks, koffs, hashes, scores, counter, st, n_sm);
+        default: return launch_accum_ring<32>(ixp, items, n_items, n_chunks, koffs, hashes, scores, counter, st, n_sm);
+    }
 }
 
 template <int LPR>
@@ -825,12 +943,12 @@ void dispatch_accum(int lpr, const DevIndex* ixp, const SlowItem* items, uint32_
     }
 }
 
-// chunk a query's k-mers into items of at most PHY_FUSED_KMAX rows
-void push_items(std::vector<SlowItem>& items, uint32_t slot, uint32_t q, uint32_t K) {
-    for (uint32_t k0 = 0; k0 < K; k0 += PHY_FUSED_KMAX) {
+// chunk a query's k-mers into items of at most `cmax` rows (what the counter planes can hold)
+void push_items(std::vector<SlowItem>& items, uint32_t slot, uint32_t q, uint32_t K, uint32_t cmax) {
+    for (uint32_t k0 = 0; k0 < K; k0 += cmax) {
         SlowItem it;
         it.slot = slot; it.query = q; it.k0 = k0;
-        it.k1 = K - k0 > PHY_FUSED_KMAX ? k0 + PHY_FUSED_KMAX : K;
+        it.k1 = K - k0 > cmax ? k0 + cmax : K;
         items.push_back(it);
     }
 }
@@ -842,16 +960,29 @@ int phy_lpr_for_stride(uint32_t stride) { return lpr_for_stride(stride); }
 // Run the general path for `slots` (query ids) against index ix; scores into d_scores.
 static int run_general(phy_ctx* ctx, const HostIndex& ix, int ipos, const std::vector<uint32_t>& slot_queries,
                        uint32_t* d_scores_out) {
+    const bool use_ring = ix.d.num_hashes == 1 && ctx->kernel_path != 1;
+    const uint32_t cmax = use_ring ? PHY_LONG_KMAX : PHY_FUSED_KMAX;
     std::vector<SlowItem> items;
-    for (uint32_t s = 0; s < slot_queries.size(); s++) push_items(items, s, slot_queries[s], ctx->h_nk[slot_queries[s]]);
+    for (uint32_t s = 0; s < slot_queries.size(); s++)
+        push_items(items, s, slot_queries[s], ctx->h_nk[slot_queries[s]], cmax);
     const size_t n_sc = slot_queries.size() * (size_t)ix.d.n_docs;
     PHY_CUDA(ctx, cudaMemsetAsync(d_scores_out, 0, n_sc * sizeof(uint32_t), ctx->stream));
     if (items.empty()) return PHY_OK;
     PHY_TRY(phy_ensure(ctx, ctx->d_items, items.size()));
     PHY_TRY(phy_h2d(ctx, ctx->d_items.p, items.data(), items.size() * sizeof(SlowItem)));
     const uint32_t n_chunks = (ix.d.stride + PHY_CHUNK_BYTES - 1) / PHY_CHUNK_BYTES;
-    dispatch_accum(ix.lpr, ctx->d_indexes.p + ipos, ctx->d_items.p, (uint32_t)items.size(), n_chunks,
-                   ctx->d_koffs.p, ctx->d_hashes.p, ctx->total_kmers, d_scores_out, ctx->stream);
+    if (use_ring) {
+        PHY_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p + 4, 0, sizeof(unsigned long long), ctx->stream));
+        if (dispatch_accum_ring(ix.lpr, ctx->d_indexes.p + ipos, ctx->d_items.p, (uint32_t)items.size(), n_chunks,
+                                ctx->d_koffs.p, ctx->d_hashes.p, d_scores_out, ctx->d_counters.p + 4, ctx->stream,
+                                ctx->n_sm) != 0) {
+            phy_set_error(ctx, "cannot configure the ring score kernel: %s", cudaGetErrorString(cudaGetLastError()));
+            return PHY_ERR_CUDA;
+        }
+    } else {
+        dispatch_accum(ix.lpr, ctx->d_indexes.p + ipos, ctx->d_items.p, (uint32_t)items.size(), n_chunks,
+                       ctx->d_koffs.p, ctx->d_hashes.p, ctx->total_kmers, d_scores_out, ctx->stream);
+    }
     ctx->launches++;
     PHY_CUDA(ctx, cudaGetLastError());
     return PHY_OK;
@@ -861,21 +992,32 @@ int phy_launch_scores(phy_ctx* ctx, int idx_id, uint32_t* d_out_scores) {
     const HostIndex& ix = ctx->idx[idx_id];
     std::vector<uint32_t> qs;
     for (uint32_t q = 0; q < ctx->nq; q++) qs.push_back(q);
+    PHY_TRY(phy_ensure(ctx, ctx->d_counters, 8));
     return run_general(ctx, ix, idx_id, qs, d_out_scores);
 }
 
 int phy_launch_gather(phy_ctx* ctx, const phy_match_params* p) {
     // per-query minimum score T (host double arithmetic, identical to the oracle / cobs)
-    std::vector<uint32_t> T(ctx->nq), fastq, slowq;
+    // fastq = fused in one kernel: K <= 1023 (10 counter planes) first, then K <= 16383 (14 planes,
+    // ring kernel only); slowq = longer queries, chunked through the dense-score path
+    std::vector<uint32_t> T(ctx->nq), fastq, midq, slowq;
+    const bool have_p14 = ctx->kernel_path == 3;
     for (uint32_t q = 0; q < ctx->nq; q++) {
         double x = p->threshold * (double)ctx->h_nk[q];
         double r = p->floor_mode ? floor(x) : ceil(x);
         T[q] = r < 0 ? 0u : (r > 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)r);
-        if (ctx->h_nk[q] == 0) continue;
-        (ctx->h_nk[q] <= PHY_FUSED_KMAX ? fastq : slowq).push_back(q);
+        const uint32_t K = ctx->h_nk[q];
+        if (K == 0) continue;
+        if (K <= PHY_FUSED_KMAX) fastq.push_back(q);
+        else if (have_p14 && K <= PHY_LONG_KMAX) midq.push_back(q);
+        else slowq.push_back(q);
     }
     // longest first: balances the tail and keeps co-resident groups of a warp similar
-    std::stable_sort(fastq.begin(), fastq.end(), [&](uint32_t a, uint32_t b) { return ctx->h_nk[a] > ctx->h_nk[b]; });
+    auto by_len = [&](uint32_t a, uint32_t b) { return ctx->h_nk[a] > ctx->h_nk[b]; };
+    std::stable_sort(fastq.begin(), fastq.end(), by_len);
+    std::stable_sort(midq.begin(), midq.end(), by_len);
+    const uint32_t n_fast10 = (uint32_t)fastq.size(), n_fast14 = (uint32_t)midq.size();
+    fastq.insert(fastq.end(), midq.begin(), midq.end());   // [P10 queries | P14 queries]
     PHY_TRY(phy_ensure(ctx, ctx->d_T, ctx->nq + 1));
     PHY_TRY(phy_h2d(ctx, ctx->d_T.p, T.data(), T.size() * sizeof(uint32_t)));
     PHY_TRY(phy_ensure(ctx, ctx->d_qlist, ctx->nq + 1));
@@ -913,7 +1055,7 @@ int phy_launch_gather(phy_ctx* ctx, const phy_match_params* p) {
         PHY_CUDA(ctx, cudaMemsetAsync(ctx->d_qcount.p, 0, (ctx->nq + 1) * sizeof(uint32_t), ctx->stream));
         GatherArgs a;
         a.indexes = ctx->d_indexes.p;
-        a.qlist = ctx->d_qlist.p; a.n_q = (uint32_t)fastq.size();
+        a.qlist = ctx->d_qlist.p; a.n_q = n_fast10;
         a.koffs = ctx->d_koffs.p; a.nk = ctx->d_nk.p; a.T = ctx->d_T.p;
         a.hashes = ctx->d_hashes.p; a.total_kmers = ctx->total_kmers;
         a.top_n = p->top_n;
@@ -941,25 +1083,25 @@ int phy_launch_gather(phy_ctx* ctx, const phy_match_params* p) {
                 for (uint32_t i : cls[c]) multi_hash |= ctx->idx[i].d.num_hashes > 1;
                 const bool ring = !multi_hash && ctx->kernel_path == 3;
                 if (ring) {  // path C: lane-private cp.async ring, persistent warps
-                    PHY_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p + 3, 0, sizeof(unsigned long long), ctx->stream));
-                    int rc = -1;
-                    switch (c) {
-                        case 0: rc = launch_ring<1, RING_NB, RING_WARPS>(a, ctx->stream, ctx->n_sm); break;
-                        case 1: rc = launch_ring<2, RING_NB, RING_WARPS>(a, ctx->stream, ctx->n_sm); break;
-                        case 2: rc = launch_ring<4, RING_NB, RING_WARPS>(a, ctx->stream, ctx->n_sm); break;
-                        case 3: rc = launch_ring<8, RING_NB, RING_WARPS>(a, ctx->stream, ctx->n_sm); break;
-                        case 4: rc = launch_ring<16, RING_NB, RING_WARPS>(a, ctx->stream, ctx->n_sm); break;
-                        default: rc = launch_ring<32, RING_NB, RING_WARPS>(a, ctx->stream, ctx->n_sm); break;
+                    for (int pass = 0; pass < 2; pass++) {   // 10-plane queries, then 14-plane queries
+                        a.qlist = ctx->d_qlist.p + (pass ? n_fast10 : 0);
+                        a.n_q = pass ? n_fast14 : n_fast10;
+                        if (a.n_q == 0) continue;
+                        PHY_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p + 3, 0, sizeof(unsigned long long), ctx->stream));
+                        int rc = pass ? dispatch_ring<14>(c, a, ctx->stream, ctx->n_sm)
+                                      : dispatch_ring<10>(c, a, ctx->stream, ctx->n_sm);
+                        if (rc != 0) {
+                            phy_set_error(ctx, "cannot configure the ring gather kernel: %s",
+                                          cudaGetErrorString(cudaGetLastError()));
+                            return PHY_ERR_CUDA;
+                        }
+                        ctx->launches++;
+                        PHY_CUDA(ctx, cudaGetLastError());
                     }
-                    if (rc != 0) {
-                        phy_set_error(ctx, "cannot configure the ring gather kernel: %s",
-                                      cudaGetErrorString(cudaGetLastError()));
-                        return PHY_ERR_CUDA;
-                    }
-                    ctx->launches++;
-                    PHY_CUDA(ctx, cudaGetLastError());
+                    a.qlist = ctx->d_qlist.p; a.n_q = n_fast10;
                     continue;
                 }
+                // paths A/B know 10 planes only: the 14-plane queries were routed to slowq above
                 const bool bulk = c >= 3 && !multi_hash && ctx->kernel_path == 2;
                 if (bulk) {  // persistent warps pull units from counters[3]
                     PHY_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p + 3, 0, sizeof(unsigned long long), ctx->stream));

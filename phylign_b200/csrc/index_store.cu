@@ -131,6 +131,29 @@ __global__ void __launch_bounds__(256) synth_build_kernel(phy_synth_spec s, uint
     }
 }
 
+// classic-construct for real sequences: OR every k-mer of query q into document doc_of_query[q]
+__global__ void __launch_bounds__(256) insert_kmers_kernel(const uint64_t* __restrict__ hashes, uint64_t total_kmers,
+                                                           const uint64_t* __restrict__ koffs, uint32_t nq,
+                                                           const uint32_t* __restrict__ doc_of_query, uint64_t sig,
+                                                           uint64_t magic, uint32_t num_hashes, uint32_t stride,
+                                                           uint32_t n_docs, uint8_t* __restrict__ rows) {
+    uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total_kmers) return;
+    uint32_t lo = 0, hi = nq;
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (koffs[mid] <= g) lo = mid; else hi = mid;
+    }
+    const uint32_t d = doc_of_query[lo];
+    if (d >= n_docs) return;
+    uint32_t* words = reinterpret_cast<uint32_t*>(rows);
+    for (uint32_t j = 0; j < num_hashes; j++) {
+        const uint32_t row = phy_fastmod(hashes[(uint64_t)j * total_kmers + g], sig, magic);
+        const uint64_t bit = (uint64_t)row * stride * 8ull + d;
+        atomicOr(&words[bit >> 5], 1u << (bit & 31));
+    }
+}
+
 __global__ void __launch_bounds__(256) synth_reads_kernel(const phy_synth_spec* __restrict__ specs,
                                                           uint32_t n_specs, uint64_t reads_seed,
                                                           uint64_t first_read, uint32_t n_reads,
@@ -209,6 +232,16 @@ int phy_synth_reads_dev(phy_ctx* ctx, const phy_synth_spec* d_specs, uint32_t n_
     unsigned blocks = (unsigned)std::min<uint64_t>(((uint64_t)n_reads + 7) / 8, 148ull * 32);
     synth_reads_kernel<<<blocks, 256, 0, ctx->stream>>>(d_specs, n_specs, reads_seed, first_read, n_reads,
                                                        read_len, random_q8, err_q16, d_out);
+    PHY_CUDA(ctx, cudaGetLastError());
+    return PHY_OK;
+}
+
+int phy_insert_kmers(phy_ctx* ctx, HostIndex& ix, const uint32_t* d_doc_of_query) {
+    if (ctx->total_kmers == 0) return PHY_OK;
+    const uint64_t nblk = (ctx->total_kmers + 255) / 256;
+    insert_kmers_kernel<<<(unsigned)nblk, 256, 0, ctx->stream>>>(ctx->d_hashes.p, ctx->total_kmers, ctx->d_koffs.p,
+                                                                ctx->nq, d_doc_of_query, ix.d.sig, ix.d.magic,
+                                                                ix.d.num_hashes, ix.d.stride, ix.d.n_docs, ix.rows_mut);
     PHY_CUDA(ctx, cudaGetLastError());
     return PHY_OK;
 }

@@ -190,6 +190,13 @@ class Matcher:
         self.indexes[idx_id] = ResidentIndex(idx_id, batch, hdr)
         return idx_id
 
+    def insert_queries(self, idx_id, doc_of_query):
+        """Test/bench utility: add the k-mers of the current queries to documents of an index
+        (`cobs classic-construct` semantics); doc 0xFFFFFFFF skips a query."""
+        a = np.ascontiguousarray(doc_of_query, dtype=np.uint32)
+        assert len(a) == self._nq
+        self._ck(self._L.phy_index_insert(self._ctx, idx_id, a.ctypes.data))
+
     def evict(self, idx_id):
         self._ck(self._L.phy_index_evict(self._ctx, idx_id))
         self.indexes.pop(idx_id, None)

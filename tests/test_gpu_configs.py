@@ -1,0 +1,111 @@
+"""BASELINE.json configs 2 and 5 at oracle-checkable sizes (needs a B200)."""
+import lzma
+import os
+import random
+
+import numpy as np
+import pytest
+
+import oracle
+from tests import helpers as H
+from tests.test_gpu_parity import _check_against_oracle, _evict_all
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def M():
+    from phylign_b200.matcher import Matcher
+    m = Matcher(0)
+    yield m
+    m.close()
+
+
+def _oracle_copy(m, idx_id, n_docs, sig):
+    oidx = oracle.OracleIndex.new(n_docs, sig)
+    oidx.body.reshape(-1)[:] = np.frombuffer(m.download_index(idx_id), dtype=np.uint8)
+    return oidx
+
+
+def test_config2_argannot_vs_4000_genomes_bit_exact_scores(M):
+    """data/ARGannot_r3.fa (after fix_query) vs one batch-sized index with planted genes:
+    all 1856 x 4000 scores bit-exact, and the -t 0.7 / top-100 lists identical."""
+    from phylign_b200 import _lib
+    _evict_all(M)
+    genes = []
+    for line in lzma.open(os.path.join(H.GOLDEN, "ARGannot_r3.fixed.fa.xz"), "rt"):
+        line = line.rstrip("\n")
+        if line.startswith(">"):
+            genes.append([line[1:], ""])
+        else:
+            genes[-1][1] += line
+    assert len(genes) == 1856 and sum(len(s) for _, s in genes) == 1650212
+    n_docs, glen = 4000, 100_000
+    sig = oracle.signature_size(glen - 30)
+    spec = _lib.SynthSpec(seed=2, n_docs=n_docs, genome_len=glen, clade_size=32, clade_sub_q16=328, doc_sub_q16=328)
+    i = M.add_synth_index("arg__01", spec, sig)
+    # plant 60 genes (whole, or their first half) into random document subsets
+    rnd = random.Random(2)
+    plant = []
+    for g in rnd.sample(range(len(genes)), 60):
+        seq = genes[g][1]
+        for d in rnd.sample(range(n_docs), rnd.choice([3, 40, 400])):
+            plant.append((seq if rnd.random() < 0.6 else seq[:len(seq) // 2], d))
+    M.set_queries([(f"p{j}", s) for j, (s, _) in enumerate(plant)])
+    M.insert_queries(i, [d for _, d in plant])
+    oidx = _oracle_copy(M, i, n_docs, sig)
+    M.set_queries(genes)
+    got = M.scores(i)
+    assert got.shape == (1856, 4000)
+    n_full = 0
+    for q, (_, s) in enumerate(genes):
+        k, want = oidx.scores(s.encode(), sliced=True, threads=8)
+        assert (got[q] == want).all(), q
+        n_full += int((want == k).sum())
+    assert n_full > 5000                      # planted copies score K: the scores span 0..K
+    res = _check_against_oracle(M, i, oidx, genes, 0.7, 100)
+    assert len(res.units) >= 60
+    _check_against_oracle(M, i, oidx, genes[:300], 0.33, 0)      # plasmid-style threshold, no top-N
+
+
+def test_config5_long_reads_threshold_sweep(M):
+    """10 kbp nanopore-like reads (8% errors, K = 9970 -> 14 planes) and plasmid-sized queries
+    (K > 16383 -> chunked general path) with the match-ratio threshold swept 0.4 .. 0.9."""
+    _evict_all(M)
+    specs, oidxs, ids = [], [], []
+    for b in range(3):
+        sp = oracle.SynthSpec(seed=50 + b, n_docs=[300, 90, 1100][b], genome_len=60_000, clade_size=8,
+                              clade_sub_q16=655, doc_sub_q16=655)
+        docs = [oracle.synth_genome(sp, d) for d in range(sp.n_docs)]
+        oi = oracle.OracleIndex.construct(docs)
+        p = f"/tmp/phy_c5_{b}.cobs_classic"
+        oi.write(p)
+        ids.append(M.load_index(p, batch=f"c5__{b:02d}"))
+        os.unlink(p)
+        specs.append(sp)
+        oidxs.append(oi)
+    records = [(f"ont{r}", oracle.synth_read(specs, 5, r, 10_000, random_q8=20, err_q16=5243).decode())
+               for r in range(60)]
+    rnd = random.Random(5)
+    for j, ln in enumerate((20_000, 33_000, 59_000)):
+        g = oracle.synth_genome(specs[j % 3], rnd.randrange(80)).decode()
+        records.append((f"plasmid{j}", g[:ln]))
+    records.append(("k16383", oracle.synth_genome(specs[0], 1).decode()[:16413]))     # last 14-plane length
+    records.append(("k16384", oracle.synth_genome(specs[0], 1).decode()[:16414]))     # first chunked length
+    M.set_queries(records)
+    for thr in (0.4, 0.5, 0.6, 0.7, 0.8, 0.9):
+        res = M.match(thr, top_n=20)
+        for i, oi in zip(ids, oidxs):
+            units = {int(u["query"]): u for u in res.units_of(i)}
+            for q, (_, s) in enumerate(records):
+                k, hits = oi.query(s.encode(), thr)
+                n_pass = len(hits)
+                if n_pass > 20:
+                    cut = hits[19][1]
+                    hits = [h for h in hits if h[1] >= cut]
+                if n_pass == 0:
+                    assert q not in units
+                else:
+                    u = units[q]
+                    assert int(u["n_pass"]) == n_pass, (thr, i, q)
+                    assert [(int(h["doc"]), int(h["score"])) for h in res.hits_of(u)] == hits, (thr, i, q)
