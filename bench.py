@@ -31,20 +31,44 @@ READS_SEED, RANDOM_Q8, ERR_Q16 = 3, 51, 655
 
 
 def workload(args):
-    w = dict(n_indexes=args.indexes, n_docs=args.docs, genome_len=args.genome_len,
-             n_reads=args.reads, read_len=args.read_len)
-    w["signature_size"] = int(math.ceil((w["genome_len"] - 30) * (-1.0 / math.log(1.0 - 0.3))))
-    w["row_size"] = (w["n_docs"] + 7) // 8
+    """Batches (indexes) + reads of the selected workload.
+
+    reads1k (default, BASELINE configs[2]): --indexes equal synthetic batches.
+    db661k (BASELINE configs[3]): the 305 batches of the 661k database, document counts and
+    decompressed sizes from the reference's data files (phylign_b200/data/db_shape.tsv),
+    content synthetic; --db-scale shrinks every signature_size (1.0 = the real 1.06 TB)."""
+    ratio = -1.0 / math.log(1.0 - 0.3)                      # cobs classic-construct: fpr 0.3, 1 hash
+    batches = []
+    if args.workload == "db661k":
+        for line in open(os.path.join(ROOT, "phylign_b200", "data", "db_shape.tsv")):
+            if line.startswith("#"):
+                continue
+            name, nbytes, docs = line.split("\t")
+            docs = int(docs)
+            sig = max(4096, int(int(nbytes) / ((docs + 7) // 8) * args.db_scale))
+            batches.append(dict(name=name, n_docs=docs, signature_size=sig,
+                                genome_len=max(1200, int(sig / ratio)), seed=1000 + len(batches)))
+    else:
+        sig = int(math.ceil((args.genome_len - 30) * ratio))
+        for i in range(args.indexes):
+            batches.append(dict(name=batch_name(i), n_docs=args.docs, signature_size=sig,
+                                genome_len=args.genome_len, seed=1000 + i))
+    w = dict(batches=batches, n_indexes=len(batches), n_docs=max(b["n_docs"] for b in batches),
+             n_reads=args.reads, read_len=args.read_len, name=args.workload)
+    w["signature_size"] = batches[0]["signature_size"]
+    w["row_bytes_per_kmer"] = sum((b["n_docs"] + 7) // 8 for b in batches)
     w["kmers_per_read"] = max(w["read_len"] - 30, 0)
     w["bases"] = w["n_reads"] * w["read_len"]
     # SURVEY.md 8(d): algorithmic bytes = sum_q K_q * sum_b h_b * ceil(D_b/8)
-    w["alg_bytes"] = w["n_reads"] * w["kmers_per_read"] * w["n_indexes"] * w["row_size"]
-    w["kmer_docs"] = w["n_reads"] * w["kmers_per_read"] * w["n_indexes"] * w["n_docs"]
+    w["alg_bytes"] = w["n_reads"] * w["kmers_per_read"] * w["row_bytes_per_kmer"]
+    w["kmer_docs"] = w["n_reads"] * w["kmers_per_read"] * sum(b["n_docs"] for b in batches)
     return w
 
 
-def spec_kwargs(i, w):
-    return dict(seed=1000 + i, n_docs=w["n_docs"], genome_len=w["genome_len"], clade_size=32,
+def spec_kwargs(b, w=None):
+    if isinstance(b, int):                                   # index number of the reads1k workload
+        b = w["batches"][b]
+    return dict(seed=b["seed"], n_docs=b["n_docs"], genome_len=b["genome_len"], clade_size=32,
                 clade_sub_q16=328, doc_sub_q16=328)
 
 
@@ -52,11 +76,28 @@ def batch_name(i):
     return f"synth_species_{i:03d}__01"
 
 
+def place(w, world, budget):
+    """LPT placement of the batches on the ranks (phylign_b200/sharding.py); one resident round."""
+    from phylign_b200 import sharding
+    bl = [sharding.Batch(b["name"], b["n_docs"], b["signature_size"]) for b in w["batches"]]
+    plan = sharding.assign(bl, world, budget)
+    if len(plan.rounds) != 1:
+        raise SystemExit(f"workload needs {len(plan.rounds)} resident rounds on {world} GPU(s): "
+                         "use more GPUs or --db-scale")
+    by_name = {b["name"]: b for b in w["batches"]}
+    return [[by_name[x.name] for x in plan.batches_of(r)] for r in range(world)], plan.imbalance
+
+
 def config_dict(w, extra=None):
-    c = {"workload": f"{w['n_reads']} synthetic {w['read_len']} bp reads vs {w['n_indexes']} synthetic "
-                     f"COBS classic indexes ({w['n_docs']} docs x {w['genome_len']} bp, k=31, h=1, fpr=0.3) "
-                     f"resident in HBM, -t {THRESHOLD}, top-{TOP_N}+ties, cross-index merge "
-                     "(BASELINE.json configs[2])",
+    if w["name"] == "db661k":
+        what = (f"{w['n_indexes']} synthetic COBS classic indexes shaped like the 661k database "
+                f"(docs and sizes per batch from data/decompressed_indexes_sizes.txt + 661k_batches.txt, "
+                f"{w['row_bytes_per_kmer']} B gathered per k-mer) (BASELINE.json configs[3])")
+    else:
+        what = (f"{w['n_indexes']} synthetic COBS classic indexes ({w['n_docs']} docs x "
+                f"{w['batches'][0]['genome_len']} bp, k=31, h=1, fpr=0.3) (BASELINE.json configs[2])")
+    c = {"workload": f"{w['n_reads']} synthetic {w['read_len']} bp reads vs {what} resident in HBM, "
+                     f"-t {THRESHOLD}, top-{TOP_N}+ties, cross-index merge",
          "n_reads": w["n_reads"], "read_len": w["read_len"], "n_indexes": w["n_indexes"],
          "docs_per_index": w["n_docs"], "threshold": THRESHOLD, "top_n": TOP_N,
          "algorithmic_bytes_per_step": w["alg_bytes"], "kmer_docs_per_step": w["kmer_docs"],
@@ -119,7 +160,7 @@ def host_cores():
 def oracle_index_from_device(m, idx_id, w):
     """Wrap a device-built synthetic index as an oracle index in host RAM (setup, untimed)."""
     import oracle
-    oidx = oracle.OracleIndex.new(w["n_docs"], w["signature_size"])
+    oidx = oracle.OracleIndex.new(w["batches"][0]["n_docs"], w["batches"][0]["signature_size"])
     body = m.download_index(idx_id)
     oidx.body.reshape(-1)[:] = np.frombuffer(body, dtype=np.uint8)
     return oidx
@@ -144,24 +185,25 @@ def run_reference(args, w, rank, world):
     oracle.build()
     cores = host_cores()
     n_sample = min(w["n_reads"], args.cpu_sample_reads)
-    specs_kw = [spec_kwargs(i, w) for i in range(w["n_indexes"])]
+    specs_kw = [spec_kwargs(b) for b in w["batches"]]
+    w0 = w["batches"][0]
     try:
         from phylign_b200 import _lib
         from phylign_b200.matcher import Matcher
         m = Matcher(int(os.environ.get("LOCAL_RANK", 0)))
-        i0 = m.add_synth_index(batch_name(0), _lib.SynthSpec(**specs_kw[0]), w["signature_size"])
+        i0 = m.add_synth_index(w0["name"], _lib.SynthSpec(**specs_kw[0]), w0["signature_size"])
         oidx = oracle_index_from_device(m, i0, w)
         raw = m.synth_reads([_lib.SynthSpec(**k) for k in specs_kw], READS_SEED, 0, n_sample, w["read_len"],
                             RANDOM_Q8, ERR_Q16)
         m.close()
         built = "index 0 and the reads synthesised on the GPU (setup only), then copied to host RAM"
     except Exception as e:  # no GPU: build the (small) workload with the oracle itself
-        if w["n_docs"] * w["genome_len"] > 5e7:
+        if w0["n_docs"] * w0["genome_len"] > 5e7:
             print(json.dumps({"impl": "reference", "unavailable": f"cannot synthesise the index without a GPU: {e}"}))
             return
         ospecs = [oracle.SynthSpec(**k) for k in specs_kw]
-        oidx = oracle.OracleIndex.construct([oracle.synth_genome(ospecs[0], d) for d in range(w["n_docs"])],
-                                            signature_size_override=w["signature_size"])
+        oidx = oracle.OracleIndex.construct([oracle.synth_genome(ospecs[0], d) for d in range(w0["n_docs"])],
+                                            signature_size_override=w0["signature_size"])
         raw = b"".join(oracle.synth_read(ospecs, READS_SEED, r, w["read_len"], RANDOM_Q8, ERR_Q16)
                        for r in range(n_sample))
         built = "index 0 and the reads built by the oracle on the CPU"
@@ -217,13 +259,15 @@ def run_ours(args, w, rank, world, local_rank):
         obj = [nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(obj, src=0)
         m.nccl_init(obj[0], rank, world)
-    specs = [_lib.SynthSpec(**spec_kwargs(i, w)) for i in range(w["n_indexes"])]
+    specs = [_lib.SynthSpec(**spec_kwargs(b)) for b in w["batches"]]
+    placement, imbalance = place(w, world, args.hbm_budget_gb * 10 ** 9)
     t_build = time.perf_counter()
-    local = [i for i in range(w["n_indexes"]) if i % world == rank]
-    ids = {i: m.add_synth_index(batch_name(i), specs[i], w["signature_size"]) for i in local}
+    local = placement[rank]
+    ids = {b["name"]: m.add_synth_index(b["name"], _lib.SynthSpec(**spec_kwargs(b)), b["signature_size"])
+           for b in local}
     m.sync()
     t_build = time.perf_counter() - t_build
-    m.set_ranks([batch_name(i) for i in range(w["n_indexes"])])
+    m.set_ranks([b["name"] for b in w["batches"]])
     L = w["read_len"]
     raw = m.synth_reads(specs, READS_SEED, 0, w["n_reads"], L, RANDOM_Q8, ERR_Q16)
     offs = np.arange(w["n_reads"] + 1, dtype=np.uint64) * L
@@ -232,7 +276,7 @@ def run_ours(args, w, rank, world, local_rank):
     pin_raw, pin_offs = PinnedBuffer(len(raw)), PinnedBuffer(offs.nbytes)
     pin_raw.array[:] = np.frombuffer(raw, dtype=np.uint8)
     pin_offs.array[:] = offs.view(np.uint8)
-    local_alg_bytes = w["n_reads"] * w["kmers_per_read"] * len(local) * w["row_size"]
+    local_alg_bytes = w["n_reads"] * w["kmers_per_read"] * sum((b["n_docs"] + 7) // 8 for b in local)
 
     # ---- device-resident throughput (`value`): queries already in HBM
     m.set_queries_raw(raw, offs)
@@ -293,11 +337,12 @@ def run_ours(args, w, rank, world, local_rank):
         m.close()
         return
     peak, peak_src = measured_peak()
-    kernel = "gather_count_ring_kernel<32,3,4>"
+    kernel = ("gather_count_ring_kernel<32,10,3,4>" if w["name"] == "reads1k" else
+              "gather_count_ring_kernel<LPR,10,3,4> (one launch per row-width class)")
     traffic = None
     try:   # DRAM bytes per launch from the committed ncu capture of this exact workload, else null
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        key = f"{kernel}|{w['n_reads']}|{w['read_len']}|{w['n_indexes']}|{w['n_docs']}|{world}"
+        key = f"{kernel}|{w['name']}|{w['n_reads']}|{w['read_len']}|{w['n_indexes']}|{w['n_docs']}|{world}"
         traffic = tj[key]["traffic_bytes"] if key in tj else None
     except Exception:
         pass
@@ -306,7 +351,8 @@ def run_ours(args, w, rank, world, local_rank):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": config_dict(w, {"sharding": f"indexes round-robin over {world} GPU(s), queries replicated",
+            "config": config_dict(w, {"sharding": f"indexes placed LPT-by-row-bytes on {world} GPU(s) "
+                                                  f"(imbalance {imbalance:.3f}), queries replicated",
                                       "index_build_s": round(t_build, 2),
                                       "kmer_docs_per_s": w["kmer_docs"] / (ms_per_step * 1e-3),
                                       "phase_ms_hash_gather_merge": [round(float(x), 3) for x in np.mean(phases, axis=0)],
@@ -328,7 +374,7 @@ def run_ours(args, w, rank, world, local_rank):
             oracle.build()
             cores = host_cores()
             n_sample = min(w["n_reads"], args.cpu_sample_reads)
-            oidx = oracle_index_from_device(m, ids[0], w)
+            oidx = oracle_index_from_device(m, ids[w["batches"][0]["name"]], w)
             reads = [raw[r * L:(r + 1) * L] for r in range(n_sample)]
             dt, mode_name, both = time_oracle(oidx, reads, cores)
             v = n_sample * L / (dt * w["n_indexes"])
@@ -357,6 +403,9 @@ def main():
     ap.add_argument("--docs", type=int, default=4000)
     ap.add_argument("--genome-len", type=int, default=1_000_000)
     ap.add_argument("--cpu-sample-reads", type=int, default=20_000)
+    ap.add_argument("--workload", default="reads1k", choices=["reads1k", "db661k"])
+    ap.add_argument("--db-scale", type=float, default=1.0, help="db661k: scale every signature_size")
+    ap.add_argument("--hbm-budget-gb", type=float, default=170.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))

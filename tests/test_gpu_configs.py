@@ -62,7 +62,7 @@ def test_config2_argannot_vs_4000_genomes_bit_exact_scores(M):
         k, want = oidx.scores(s.encode(), sliced=True, threads=8)
         assert (got[q] == want).all(), q
         n_full += int((want == k).sum())
-    assert n_full > 5000                      # planted copies score K: the scores span 0..K
+    assert n_full > 2000                      # planted copies score K: the scores span 0..K
     res = _check_against_oracle(M, i, oidx, genes, 0.7, 100)
     assert len(res.units) >= 60
     _check_against_oracle(M, i, oidx, genes[:300], 0.33, 0)      # plasmid-style threshold, no top-N
