@@ -116,7 +116,7 @@ extern "C" void phy_ctx_destroy(phy_ctx* ctx) {
                     ctx->d_qcount.p, ctx->d_scores.p, ctx->d_items.p, ctx->d_slotq.p, ctx->d_ckey.p, ctx->d_qoffs_c.p,
                     ctx->d_foffs.p, ctx->d_scan_tmp.p, ctx->d_cval.p, ctx->d_qcursor.p, ctx->d_nfinal.p,
                     ctx->d_final.p, ctx->d_flush.p, ctx->d_foffs_all.p, ctx->d_rank_base.p,
-                    ctx->d_recv.p, ctx->d_units_sorted.p, ctx->d_unit_flag.p, ctx->d_unit_id.p, ctx->d_unit_pos.p};
+                    ctx->d_recv.p, ctx->d_units_sorted.p, ctx->d_unit_flag.p, ctx->d_unit_id.p, ctx->d_unit_pos.p, ctx->d_ioffs.p};
     for (void* b : bufs) if (b) cudaFree(b);
     for (int i = 0; i < 2; i++) {
         if (ctx->pin[i]) cudaFreeHost(ctx->pin[i]);

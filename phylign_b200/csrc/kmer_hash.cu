@@ -110,6 +110,63 @@ __global__ void __launch_bounds__(256) kmer_hash_kernel(
     for (uint32_t j = 0; j < num_hashes; j++) hashes[(uint64_t)j * total_kmers + g] = xxh64_packed(w, k, j);
 }
 
+// k = 31 fast path: one thread rolls over 4 consecutive k-mers of one query (34 byte loads
+// for 4 k-mers instead of 124) and turns the canonical 2-bit value into its 31 ASCII bytes
+// with a 256-entry shared-memory table (4 bases -> 4 letters per lookup).
+constexpr int KPT = 4;  // k-mers per thread
+__global__ void __launch_bounds__(256) kmer_hash31_roll_kernel(
+    const char* __restrict__ seq, const uint64_t* __restrict__ qoffs, const uint64_t* __restrict__ koffs,
+    const uint64_t* __restrict__ ioffs, uint32_t nq, uint64_t total_items, uint64_t total_kmers,
+    int canonicalize, uint32_t num_hashes, uint64_t* __restrict__ hashes, unsigned long long* __restrict__ err) {
+    __shared__ uint32_t lut[256];
+    {
+        const uint32_t b = threadIdx.x;  // 4 bases MSB-first -> 4 ASCII bytes, first base in the low byte
+        uint32_t v = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) v |= ((0x54474341u >> (8 * ((b >> (6 - 2 * i)) & 3u))) & 0xFFu) << (8 * i);
+        lut[b] = v;
+    }
+    __syncthreads();
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total_items) return;
+    uint32_t lo = 0, hi = nq;  // ioffs[lo] <= t < ioffs[hi]
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(&ioffs[mid]) <= t) lo = mid; else hi = mid;
+    }
+    const uint32_t q = lo;
+    const uint64_t k0 = __ldg(&koffs[q]);
+    const uint32_t K = (uint32_t)(__ldg(&koffs[q + 1]) - k0);
+    const uint32_t i0 = (uint32_t)(t - __ldg(&ioffs[q])) * KPT;
+    const uint32_t n = min((uint32_t)KPT, K - i0);
+    const char* s = seq + __ldg(&qoffs[q]) + i0;
+    const uint64_t mask = (1ULL << 62) - 1;
+    uint64_t fwd = 0, rc = 0;
+    bool bad = false;
+#pragma unroll
+    for (int i = 0; i < 30 + KPT; i++) {
+        if (i < 30 + (int)n) {
+            const uint32_t c = (uint8_t)__ldg(&s[i]);
+            const uint32_t x = (c >> 1) & 3u;
+            const uint32_t code = x ^ (x >> 1);  // A0 C1 G2 T3
+            bad |= ((0x54474341u >> (8 * code)) & 0xFFu) != c;
+            fwd = ((fwd << 2) | code) & mask;
+            rc = (rc >> 2) | ((uint64_t)(3u - code) << 60);
+            if (i >= 30) {
+                const uint64_t v = ((canonicalize && rc < fwd) ? rc : fwd) << 2;  // 31 bases + 1 pad = 8 groups of 4
+                uint64_t w[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    w[j] = (uint64_t)lut[(v >> (56 - 16 * j)) & 0xFF] | ((uint64_t)lut[(v >> (48 - 16 * j)) & 0xFF] << 32);
+                w[3] &= 0x00FFFFFFFFFFFFFFULL;  // drop the pad letter
+                const uint64_t g = k0 + i0 + (uint32_t)(i - 30);
+                for (uint32_t j = 0; j < num_hashes; j++) hashes[(uint64_t)j * total_kmers + g] = xxh64_packed(w, 31, j);
+            }
+        }
+    }
+    if (bad) report_bad(err, q);
+}
+
 }  // namespace
 
 int phy_launch_hash(phy_ctx* ctx) {
@@ -127,8 +184,19 @@ int phy_launch_hash(phy_ctx* ctx) {
         return PHY_ERR_ARG;
     }
     if (ctx->q_term_size == 31) {
-        kmer_hash_kernel<31><<<(unsigned)nblk, 256, 0, ctx->stream>>>(
-            ctx->d_seq.p, ctx->d_qoffs.p, ctx->d_koffs.p, ctx->nq, ctx->total_kmers, 31,
+        // work items = runs of KPT consecutive k-mers of one query
+        std::vector<uint64_t> ioffs(ctx->nq + 1);
+        uint64_t run = 0;
+        for (uint32_t q = 0; q < ctx->nq; q++) {
+            ioffs[q] = run;
+            run += (ctx->h_nk[q] + KPT - 1) / KPT;
+        }
+        ioffs[ctx->nq] = run;
+        PHY_TRY(phy_ensure(ctx, ctx->d_ioffs, ctx->nq + 2));
+        PHY_TRY(phy_h2d(ctx, ctx->d_ioffs.p, ioffs.data(), ioffs.size() * sizeof(uint64_t)));
+        const uint64_t nb = (run + 255) / 256;
+        kmer_hash31_roll_kernel<<<(unsigned)nb, 256, 0, ctx->stream>>>(
+            ctx->d_seq.p, ctx->d_qoffs.p, ctx->d_koffs.p, ctx->d_ioffs.p, ctx->nq, run, ctx->total_kmers,
             (int)ctx->q_canon, nh, ctx->d_hashes.p, ctx->d_counters.p + 2);
     } else {
         kmer_hash_kernel<0><<<(unsigned)nblk, 256, 0, ctx->stream>>>(

@@ -79,7 +79,7 @@ struct phy_ctx {
     std::vector<uint64_t> h_qoffs, h_koffs;
     std::vector<uint32_t> h_nk;
     DevBuf<char> d_seq;
-    DevBuf<uint64_t> d_qoffs, d_koffs, d_hashes;
+    DevBuf<uint64_t> d_qoffs, d_koffs, d_hashes, d_ioffs;
     DevBuf<uint32_t> d_nk, d_T, d_qlist, d_class;
     bool hashes_valid = false;
 
