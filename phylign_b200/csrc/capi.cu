@@ -341,11 +341,21 @@ extern "C" int phy_index_push(phy_ctx* ctx, int idx_id, const void* host_chunk, 
     }
     PHY_CUDA(ctx, cudaSetDevice(ctx->device));
     const uint8_t* s = (const uint8_t*)host_chunk;
+    const bool pinned_src = nbytes >= (1u << 16) && is_pinned(host_chunk);
     while (nbytes) {
         size_t n = (size_t)std::min<uint64_t>(nbytes, ctx->pin_bytes);
         int slot = ctx->pin_cur;
         ctx->pin_cur ^= 1;
         PHY_CUDA(ctx, cudaEventSynchronize(ctx->pin_ev[slot]));
+        if (pinned_src) {  // caller's buffer is page-locked (phy_host_alloc): DMA straight from it
+            PHY_CUDA(ctx, cudaMemcpyAsync(ctx->d_stage[slot], s, n, cudaMemcpyHostToDevice, ctx->stream));
+            PHY_CUDA(ctx, cudaEventRecord(ctx->ev_t1, ctx->stream));
+            PHY_TRY(phy_restride_chunk(ctx, *ix, ctx->d_stage[slot], ix->pushed, n));
+            PHY_CUDA(ctx, cudaEventRecord(ctx->pin_ev[slot], ctx->stream));
+            PHY_CUDA(ctx, cudaEventSynchronize(ctx->ev_t1));  // the caller may refill its buffer now
+            ix->pushed += n; s += n; nbytes -= n; ctx->h2d_bytes += n;
+            continue;
+        }
         memcpy(ctx->pin[slot], s, n);
         PHY_CUDA(ctx, cudaMemcpyAsync(ctx->d_stage[slot], ctx->pin[slot], n, cudaMemcpyHostToDevice, ctx->stream));
         PHY_TRY(phy_restride_chunk(ctx, *ix, ctx->d_stage[slot], ix->pushed, n));

@@ -8,7 +8,7 @@ from phylign_b200 import _lib
 from phylign_b200.matcher import Matcher, PinnedBuffer
 
 n_idx = int(sys.argv[1]) if len(sys.argv) > 1 else 8
-args = bench.argparse.Namespace(indexes=n_idx, docs=4000, genome_len=1_000_000, reads=100_000, read_len=1000)
+args = bench.argparse.Namespace(workload="reads1k", db_scale=1.0, indexes=n_idx, docs=4000, genome_len=1_000_000, reads=100_000, read_len=1000)
 w = bench.workload(args)
 m = Matcher(0)
 specs = [_lib.SynthSpec(**bench.spec_kwargs(i, w)) for i in range(n_idx)]
