@@ -168,6 +168,20 @@ def cmd_match_db(a):
                 p = line.split()
                 if len(p) >= 2:
                     sizes[os.path.basename(p[0]).replace(".cobs_classic.xz", "")] = int(p[1])
+    if a.shard:
+        from . import sharding
+        i, n = (int(x) for x in a.shard.split("/"))
+        if not sizes:
+            _die("--shard needs --index-sizes-table")
+        docs_of = {}
+        for b in batches:     # document counts come from the index headers (cheap: first bytes of the xz)
+            from .cobs_index import IndexStream
+            path = os.path.join(a.cobs_dir, f"{b}.cobs_classic.xz")
+            st = IndexStream(path if os.path.exists(path) else path[:-3])
+            docs_of[b] = (st.header.n_docs, st.header.signature_size)
+            st.abort()
+        plan = sharding.assign([sharding.Batch(b, *docs_of[b]) for b in batches], n, 170 * 10 ** 9)
+        batches = sorted(x.name for rnd in plan.rounds for x in rnd[i])
     merged_inputs = []
     with Matcher(a.device, a.hbm_budget) as m:
         m.set_queries(records)
@@ -254,6 +268,10 @@ def build_parser():
     f.add_argument("--device", type=int, default=0)
     f.set_defaults(fn=cmd_filter)
 
+    fq = sub.add_parser("fix-query", help="seqtk seq -A -U -C | awk non-ACGT->A (Snakefile:326-332), all inputs concatenated")
+    fq.add_argument("inputs", nargs="+")
+    fq.set_defaults(fn=lambda a: sys.stdout.write("".join(fasta.fix_query_file(p) for p in a.inputs)))
+
     d = sub.add_parser("match-db")
     d.add_argument("--cobs-dir", required=True)
     d.add_argument("--batches", required=True, help="file with one batch name per line (config.yaml: batches)")
@@ -267,6 +285,9 @@ def build_parser():
     d.add_argument("--index-sizes-table", default=None, help="data/decompressed_indexes_sizes.txt (verified)")
     d.add_argument("--resume", action="store_true", help="skip batches whose match file exists")
     d.add_argument("--hbm-budget", type=int, default=0)
+    d.add_argument("--shard", default=None, metavar="I/N",
+                   help="process only the batches the LPT plan gives to GPU I of N (one process per GPU; "
+                        "needs --index-sizes-table for the sizes); run `filter` over all match files afterwards")
     d.add_argument("--device", type=int, default=0)
     d.set_defaults(fn=cmd_match_db)
     return ap

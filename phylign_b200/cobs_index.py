@@ -152,6 +152,17 @@ class IndexStream:
                 if rc != 0:
                     raise IndexFormatError(f"xzcat failed on {self.path} (exit {rc})")
 
+    def abort(self):
+        """Stop reading (header-only use): close the stream and reap the decoder."""
+        try:
+            self._f.close()
+            if self._proc is not None:
+                self._proc.kill()
+                self._proc.wait()
+                self._proc = None
+        except Exception:
+            pass
+
     def __enter__(self):
         return self
 

@@ -20,6 +20,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 namespace {
 
@@ -1013,9 +1014,19 @@ int phy_launch_gather(phy_ctx* ctx, const phy_match_params* p) {
         else slowq.push_back(q);
     }
     // longest first: balances the tail and keeps co-resident groups of a warp similar
-    auto by_len = [&](uint32_t a, uint32_t b) { return ctx->h_nk[a] > ctx->h_nk[b]; };
-    std::stable_sort(fastq.begin(), fastq.end(), by_len);
-    std::stable_sort(midq.begin(), midq.end(), by_len);
+    auto sort_by_len_desc = [&](std::vector<uint32_t>& v) {  // stable counting sort: K <= 16383
+        if (v.size() < 2) return;
+        uint32_t kmin = 0xFFFFFFFFu, kmax = 0;
+        for (uint32_t q : v) { kmin = std::min(kmin, ctx->h_nk[q]); kmax = std::max(kmax, ctx->h_nk[q]); }
+        if (kmin == kmax) return;  // all reads equally long (the common case): nothing to do
+        std::vector<uint32_t> start(kmax - kmin + 2, 0), out(v.size());
+        for (uint32_t q : v) start[kmax - ctx->h_nk[q] + 1]++;
+        for (size_t i = 1; i < start.size(); i++) start[i] += start[i - 1];
+        for (uint32_t q : v) out[start[kmax - ctx->h_nk[q]]++] = q;
+        v.swap(out);
+    };
+    sort_by_len_desc(fastq);
+    sort_by_len_desc(midq);
     const uint32_t n_fast10 = (uint32_t)fastq.size(), n_fast14 = (uint32_t)midq.size();
     fastq.insert(fastq.end(), midq.begin(), midq.end());   // [P10 queries | P14 queries]
     PHY_TRY(phy_ensure(ctx, ctx->d_T, ctx->nq + 1));
@@ -1048,6 +1059,9 @@ int phy_launch_gather(phy_ctx* ctx, const phy_match_params* p) {
     uint64_t units_cap = ctx->d_units.cap, hits_cap = ctx->d_hits.cap;
     if (units_cap < 4096) units_cap = 1 << 16;
     if (hits_cap < 4096) hits_cap = 1 << 20;
+    if (const char* e = getenv("PHY_TEST_TINY_CAPS")) {  // tests: force the overflow -> regrow -> rerun path
+        if (atoi(e) && !ctx->d_units.p) { units_cap = 4; hits_cap = 4; }
+    }
     for (int attempt = 0; attempt < 3; attempt++) {
         PHY_TRY(phy_ensure(ctx, ctx->d_units, units_cap));
         PHY_TRY(phy_ensure(ctx, ctx->d_hits, hits_cap));

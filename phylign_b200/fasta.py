@@ -73,3 +73,21 @@ def read_fastx(path):
             elif last is None:
                 break
     return recs
+
+
+# ---- query preparation ---------------------------------------------------------
+# What /root/reference/Snakefile:326-332 does with `seqtk seq -A -U -C | awk gsub(/[^ACGT]/,"A")`:
+# FASTA out, one line per sequence, upper case, comments dropped, every other letter -> A.
+_FIX = bytes((c if chr(c) in "ACGT" else ord("A")) for c in
+             (ord(chr(b).upper()) if b < 128 else b for b in range(256)))
+
+
+def fix_query_seq(seq) -> str:
+    """Upper-case and replace everything outside ACGT by 'A' (table driven, C speed)."""
+    b = seq.encode() if isinstance(seq, str) else bytes(seq)
+    return b.translate(_FIX).decode()
+
+
+def fix_query_file(path) -> str:
+    """The content of intermediate/00_queries_preprocessed/{qfile}.fa for one input file."""
+    return "".join(f">{name}\n{fix_query_seq(seq)}\n" for name, seq in read_fastx(path))

@@ -147,3 +147,19 @@ def test_run_cobs_streaming_usage_error():
     r = subprocess.run([os.path.join(ROOT, "scripts", "run_cobs_streaming.sh"), "0.7", "1"],
                        capture_output=True, text=True)
     assert r.returncode == 1 and "usage:" in r.stderr and "kmer_thres threads cobs_index.xz" in r.stderr
+
+
+def test_fix_query_matches_snakefile_rule(tmp_path):
+    """fix-query == `seqtk seq -A -U -C | awk gsub(/[^ACGT]/,"A")` (Snakefile:326-332)."""
+    from phylign_b200.fasta import fix_query_file, fix_query_seq
+    assert fix_query_seq("acgtNnRyACGT-*") == "ACGTAAAAACGTAA"
+    fq = tmp_path / "r.fq"
+    fq.write_text("@r1 some comment\nacgtnACGT\n+\nIIIIIIIII\n@r2\nGGNN\n+\nIIII\n")
+    fa = tmp_path / "g.fa"
+    fa.write_text(">g1 desc\nACGT\nryk\n>g2\nTTTT\n")
+    assert fix_query_file(fq) == ">r1\nACGTAACGT\n>r2\nGGAA\n"
+    assert fix_query_file(fa) == ">g1\nACGTAAA\n>g2\nTTTT\n"
+    # the committed ARGannot fixture was produced with exactly this transform
+    import lzma
+    txt = lzma.open(os.path.join(H.GOLDEN, "ARGannot_r3.fixed.fa.xz"), "rt").read()
+    assert set("".join(l for l in txt.splitlines() if not l.startswith(">"))) == set("ACGT")
