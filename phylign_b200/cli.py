@@ -168,49 +168,42 @@ def cmd_match_db(a):
                 p = line.split()
                 if len(p) >= 2:
                     sizes[os.path.basename(p[0]).replace(".cobs_classic.xz", "")] = int(p[1])
+    from . import sharding
+    from .cobs_index import IndexStream
+
+    def path_of(b):
+        p = os.path.join(a.cobs_dir, f"{b}.cobs_classic.xz")
+        return p if os.path.exists(p) else p[:-3]
+
+    merged_inputs, todo = [], []
+    for b in batches:
+        out = os.path.join(a.match_dir, f"{b}____{qfile}.gz")
+        if a.resume and os.path.exists(out):                  # file-granular resume like Snakemake
+            merged_inputs.append(out)
+        else:
+            todo.append(b)
+    shapes = {}
+    for b in todo:      # shapes come from the index headers (the first bytes of each xz stream)
+        if not os.path.exists(path_of(b)):
+            _die(f"index of batch {b} not found under {a.cobs_dir}")
+        st = IndexStream(path_of(b))
+        h = st.header
+        st.abort()
+        shapes[b] = sharding.Batch(b, h.n_docs, h.signature_size)
+        if b in sizes and sizes[b] != h.header_size + h.body_size:
+            _die(f"{b}: decompressed size {h.header_size + h.body_size} != table {sizes[b]}")
+    n_shards, shard = 1, 0
     if a.shard:
-        from . import sharding
-        i, n = (int(x) for x in a.shard.split("/"))
-        if not sizes:
-            _die("--shard needs --index-sizes-table")
-        docs_of = {}
-        for b in batches:     # document counts come from the index headers (cheap: first bytes of the xz)
-            from .cobs_index import IndexStream
-            path = os.path.join(a.cobs_dir, f"{b}.cobs_classic.xz")
-            st = IndexStream(path if os.path.exists(path) else path[:-3])
-            docs_of[b] = (st.header.n_docs, st.header.signature_size)
-            st.abort()
-        plan = sharding.assign([sharding.Batch(b, *docs_of[b]) for b in batches], n, 170 * 10 ** 9)
-        batches = sorted(x.name for rnd in plan.rounds for x in rnd[i])
-    merged_inputs = []
+        shard, n_shards = (int(x) for x in a.shard.split("/"))
+    budget = a.hbm_budget or 160 * 10 ** 9
+    plan = sharding.assign([shapes[b] for b in todo], n_shards, budget) if todo else sharding.Plan(n_shards)
     with Matcher(a.device, a.hbm_budget) as m:
         m.set_queries(records)
-        pending = list(batches)
-        while pending:
-            loaded = []
-            while pending:                                    # fill HBM, then run, then evict
-                b = pending[0]
-                path = os.path.join(a.cobs_dir, f"{b}.cobs_classic.xz")
-                if not os.path.exists(path):
-                    path = path[:-3]
-                out = os.path.join(a.match_dir, f"{b}____{qfile}.gz")
-                if a.resume and os.path.exists(out):          # file-granular resume like Snakemake
-                    pending.pop(0)
-                    merged_inputs.append(out)
-                    continue
-                try:
-                    idx = m.load_index(path, batch=b)
-                except Exception as e:
-                    if loaded and "PHY_ERR_NOMEM" in str(e):
-                        break                                  # does not fit beside the others: next round
-                    raise
-                hdr = m.indexes[idx].header
-                if b in sizes and sizes[b] != hdr.header_size + hdr.body_size:
-                    _die(f"{b}: decompressed size {hdr.header_size + hdr.body_size} != table {sizes[b]}")
-                loaded.append(idx)
-                pending.pop(0)
-            if not loaded:
+        for rnd in plan.rounds:                               # resident round: load, match, write, evict
+            mine = sorted(x.name for x in rnd[shard])
+            if not mine:
                 continue
+            loaded = m.load_indexes([path_of(b) for b in mine], mine, workers=a.load_workers)
             res = m.match(a.t, top_n=a.n, floor_mode=a.floor)
             for idx in loaded:
                 ix = m.indexes[idx]
@@ -286,8 +279,9 @@ def build_parser():
     d.add_argument("--resume", action="store_true", help="skip batches whose match file exists")
     d.add_argument("--hbm-budget", type=int, default=0)
     d.add_argument("--shard", default=None, metavar="I/N",
-                   help="process only the batches the LPT plan gives to GPU I of N (one process per GPU; "
-                        "needs --index-sizes-table for the sizes); run `filter` over all match files afterwards")
+                   help="process only the batches the LPT plan gives to GPU I of N (one process per GPU); "
+                        "run `filter` over all match files afterwards")
+    d.add_argument("--load-workers", type=int, default=8, help="concurrent xz decoders while loading")
     d.add_argument("--device", type=int, default=0)
     d.set_defaults(fn=cmd_match_db)
     return ap

@@ -73,3 +73,28 @@ def test_match_db_writes_all_rule_outputs(tmp_path):
     r = _run([sys.executable, "-m", "phylign_b200.cli", "match-db", "--cobs-dir", H.GOLDEN, "--batches",
               str(batches), "-q", os.path.join(H.GOLDEN, "queries.fa"), "--match-dir", str(tmp_path / "x")])
     assert r.returncode != 0 and not os.listdir(tmp_path / "x")
+
+
+def test_match_db_shards_cover_all_batches(tmp_path):
+    """Two `--shard i/2` processes (one per GPU in production) write disjoint match files whose
+    union is complete; the reference's own merge step then reproduces 04_filter."""
+    batches = tmp_path / "batches.txt"
+    batches.write_text("\n".join(H.GOLDEN_BATCHES) + "\n")
+    mdir = tmp_path / "03_match"
+    for i in range(2):
+        r = _run([sys.executable, "-m", "phylign_b200.cli", "match-db", "--cobs-dir", H.GOLDEN, "--batches",
+                  str(batches), "-q", os.path.join(H.GOLDEN, "queries.fa"), "--match-dir", str(mdir),
+                  "-t", "0.7", "-n", "100", "--shard", f"{i}/2"])
+        assert r.returncode == 0, r.stderr
+        assert 1 <= len(os.listdir(mdir)) <= 3
+    assert sorted(os.listdir(mdir)) == sorted(f"{b}____queries.gz" for b in H.GOLDEN_BATCHES)
+    files = [str(mdir / f"{b}____queries.gz") for b in H.GOLDEN_BATCHES]
+    r = _run([sys.executable, os.path.join(ROOT, "scripts", "filter_queries_gpu.py"), "-n", "100",
+              "-q", os.path.join(H.GOLDEN, "queries.fa")] + files)
+    assert r.returncode == 0 and r.stdout == H.golden_filter_fa(100)
+    # resume: nothing to do, outputs untouched
+    before = {f: os.path.getmtime(mdir / f) for f in os.listdir(mdir)}
+    r = _run([sys.executable, "-m", "phylign_b200.cli", "match-db", "--cobs-dir", H.GOLDEN, "--batches",
+              str(batches), "-q", os.path.join(H.GOLDEN, "queries.fa"), "--match-dir", str(mdir),
+              "-t", "0.7", "-n", "100", "--resume"])
+    assert r.returncode == 0 and before == {f: os.path.getmtime(mdir / f) for f in os.listdir(mdir)}
