@@ -152,6 +152,24 @@ void phy_merged_free(phy_merged* m);
 int phy_merge_host(phy_ctx* ctx, uint32_t n_queries, uint32_t top_n, const uint64_t* offs,
                    const phy_cand* cands);
 
+/* ------------------------------------------------------------------ text output
+ * Host-side formatters (no GPU work) so drivers need no per-line loops.
+ * phy_format_cobs_text: what `cobs query` prints for index idx_id: per query
+ *   "*<header>\t<n_pass>\n" then "<doc name>\t<score>\n" lines; skip[q] != 0 drops the block
+ *   (records without sequence); strip_prefix writes names as postprocess_cobs.py:16-18 does.
+ *   headers/names are concatenated strings with offsets [n+1].
+ * phy_format_filter_fasta: filter_queries.py:152-156 ">{qname} {ref1,ref2,...}\n{seq}\n";
+ *   ref_names[b]/ref_offs[b]/ref_counts[b] describe the accessions of batch_rank b by doc id.
+ * Buffers are released with phy_text_free. */
+int phy_format_cobs_text(const phy_results* r, uint32_t idx_id, const char* headers, const uint64_t* hoffs,
+                         const uint8_t* skip, const char* names, const uint64_t* noffs, uint32_t n_docs,
+                         int strip_prefix, char** out, uint64_t* out_len);
+int phy_format_filter_fasta(const phy_merged* m, const char* qnames, const uint64_t* qnoffs,
+                            const char* seqs, const uint64_t* soffs, uint32_t n_batches,
+                            const char* const* ref_names, const uint64_t* const* ref_offs,
+                            const uint32_t* ref_counts, char** out, uint64_t* out_len);
+void phy_text_free(char* p);
+
 /* ------------------------------------------------------------------- multi-GPU */
 #define PHY_NCCL_ID_BYTES 128
 int phy_nccl_unique_id(void* id_out /* PHY_NCCL_ID_BYTES */);

@@ -30,7 +30,7 @@ import numpy as np
 
 from . import fasta
 from .cobs_index import ref_of
-from .cobs_text import format_cobs_text, format_filter_fasta
+from .cobs_text import format_cobs_text_fast, format_filter_fasta_fast
 
 
 def _die(msg, code=1):
@@ -68,8 +68,8 @@ def cmd_cobs_query(a):
             _die(f"--index-sizes {a.index_sizes} != header {hdr.header_size} + body {hdr.body_size}")
         m.set_queries(records)
         res = m.match(a.t, top_n=a.top_n, floor_mode=a.floor)
-        sys.stdout.write(format_cobs_text(records, res, m.indexes[idx], strip_prefix=a.top_n > 0))
-    sys.stdout.flush()
+        sys.stdout.buffer.write(format_cobs_text_fast(records, res, m.indexes[idx], strip_prefix=a.top_n > 0))
+    sys.stdout.buffer.flush()
 
 
 # ------------------------------------------------------------------------------------ filter
@@ -127,7 +127,7 @@ def merge_match_files(m, query_fn, match_fns, keep: int, log=sys.stderr) -> str:
     cands = np.array(flat, dtype=CAND_DT) if flat else np.zeros(0, CAND_DT)
     moffs, mc = m.merge_host(offs, cands, keep)
     refs_by_rank = {brank[b]: refs_sorted[b] for b in batch_names}
-    return format_filter_fasta(list(queries.items()), moffs, mc, refs_by_rank)
+    return format_filter_fasta_fast(list(queries.items()), m._merged_owner.ptr, refs_by_rank).decode()
 
 
 def cmd_filter(a):
@@ -207,9 +207,9 @@ def cmd_match_db(a):
             res = m.match(a.t, top_n=a.n, floor_mode=a.floor)
             for idx in loaded:
                 ix = m.indexes[idx]
-                text = format_cobs_text(records, res, ix, strip_prefix=True)
+                text = format_cobs_text_fast(records, res, ix, strip_prefix=True)
                 out = os.path.join(a.match_dir, f"{ix.batch}____{qfile}.gz")
-                _atomic_write(out, text.encode(), gz=True)
+                _atomic_write(out, text, gz=True)
                 merged_inputs.append(out)
                 print(f"[match-db] {ix.batch}: {len(res.units_of(idx))} queries with hits", file=sys.stderr)
             for idx in loaded:

@@ -46,3 +46,57 @@ def format_filter_fasta(records, offs, cands, ref_names_by_rank) -> str:
         refs = [ref_names_by_rank[br[i]][dc[i]] for i in range(o[q], o[q + 1])]
         out.append(f">{qname} {','.join(refs)}\n{seq}\n")
     return "".join(out)
+
+
+# ---- fast paths: the same two formats produced by the library's C++ formatters -----------------
+def _cat(strings):
+    """(concatenated bytes, uint64 offsets[n+1]) of a list of str/bytes."""
+    bs = [x if isinstance(x, bytes) else x.encode() for x in strings]
+    offs = np.zeros(len(bs) + 1, dtype=np.uint64)
+    if bs:
+        offs[1:] = np.cumsum([len(b) for b in bs], dtype=np.uint64)
+    return b"".join(bs), offs
+
+
+def format_cobs_text_fast(records, result, index, strip_prefix: bool = False, results_ptr=None) -> bytes:
+    """Same bytes as format_cobs_text(...).encode(), via phy_format_cobs_text.
+    `results_ptr`: ctypes POINTER(Results) (defaults to the one backing `result`)."""
+    import ctypes as C
+    from . import _lib
+    L = _lib.load()
+    rp = results_ptr if results_ptr is not None else result._owner.ptr
+    hcat, hoffs = _cat([h for h, _ in records])
+    skip = np.array([len(s) == 0 for _, s in records], dtype=np.uint8)
+    if not hasattr(index, "_names_cat"):
+        index._names_cat = _cat(index.doc_names)
+    ncat, noffs = index._names_cat
+    out, n = C.c_void_p(), C.c_uint64()
+    _lib.check(L.phy_format_cobs_text(rp, index.idx_id, hcat, hoffs.ctypes.data, skip.ctypes.data, ncat,
+                                      noffs.ctypes.data, len(index.doc_names), int(strip_prefix),
+                                      C.byref(out), C.byref(n)))
+    try:
+        return C.string_at(out, n.value)
+    finally:
+        L.phy_text_free(out)
+
+
+def format_filter_fasta_fast(records, merged_ptr, ref_names_by_rank) -> bytes:
+    """Same bytes as format_filter_fasta(...).encode(), via phy_format_filter_fasta.
+    `merged_ptr`: ctypes POINTER(Merged); ref_names_by_rank[batch_rank][doc] = accession."""
+    import ctypes as C
+    from . import _lib
+    L = _lib.load()
+    qcat, qoffs = _cat([q for q, _ in records])
+    scat, soffs = _cat([s for _, s in records])
+    nb = (max(ref_names_by_rank) + 1) if ref_names_by_rank else 0
+    cats = [_cat(ref_names_by_rank.get(b, [])) for b in range(nb)]
+    name_ptrs = (C.c_char_p * max(nb, 1))(*[c for c, _ in cats])
+    off_ptrs = (C.c_void_p * max(nb, 1))(*[o.ctypes.data for _, o in cats])
+    counts = np.array([len(ref_names_by_rank.get(b, [])) for b in range(nb)] or [0], dtype=np.uint32)
+    out, n = C.c_void_p(), C.c_uint64()
+    _lib.check(L.phy_format_filter_fasta(merged_ptr, qcat, qoffs.ctypes.data, scat, soffs.ctypes.data, nb,
+                                         name_ptrs, off_ptrs, counts.ctypes.data, C.byref(out), C.byref(n)))
+    try:
+        return C.string_at(out, n.value)
+    finally:
+        L.phy_text_free(out)

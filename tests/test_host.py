@@ -163,3 +163,50 @@ def test_fix_query_matches_snakefile_rule(tmp_path):
     import lzma
     txt = lzma.open(os.path.join(H.GOLDEN, "ARGannot_r3.fixed.fa.xz"), "rt").read()
     assert set("".join(l for l in txt.splitlines() if not l.startswith(">"))) == set("ACGT")
+
+
+def test_c_formatters_equal_python_formatters():
+    """phy_format_cobs_text / phy_format_filter_fasta (C++, host only) == the pure-Python
+    formatters, on fabricated result structs (no GPU involved)."""
+    import ctypes as C
+    from phylign_b200 import _lib
+    from phylign_b200.cobs_index import ClassicHeader
+    from phylign_b200.cobs_text import (format_cobs_text, format_cobs_text_fast, format_filter_fasta,
+                                        format_filter_fasta_fast)
+    from phylign_b200.matcher import CAND_DT, HIT_DT, UNIT_DT, MatchResult, ResidentIndex
+    import random
+    rnd = random.Random(3)
+    n_docs, nq = 37, 50
+    names = [f"{rnd.randrange(10**6):06d}_ACC{d:04d}" for d in range(n_docs)] 
+    names[5] = "nounderscore"          # remove_rnd_id on such a name yields "_" (SURVEY App. F.2)
+    ixs = [ResidentIndex(i, f"b__0{i}", ClassicHeader(31, 1, n_docs, 10, 1, names)) for i in (0, 2)]
+    recs = [(f"q{q} comment {q}", "" if q % 11 == 0 else "ACGT" * 10) for q in range(nq)]
+    units, hits = [], []
+    for i in (0, 2):
+        for q in range(nq):
+            if rnd.random() < 0.5 and recs[q][1]:
+                k = rnd.randrange(1, 9)
+                units.append((q, i, k + rnd.randrange(3), k, len(hits)))
+                hits += [(rnd.randrange(n_docs), rnd.randrange(1, 999999)) for _ in range(k)]
+    ua, ha = np.array(units, dtype=UNIT_DT), np.array(hits, dtype=HIT_DT)
+    nk = np.zeros(nq, np.uint32)
+    res = MatchResult(ua, ha, nk, nq, 0, 0)
+    r = _lib.Results(nq, 2, len(ua), C.cast(ua.ctypes.data, C.POINTER(_lib.Unit)), len(ha),
+                     C.cast(ha.ctypes.data, C.POINTER(_lib.Hit)), C.cast(nk.ctypes.data, C.POINTER(C.c_uint32)), 0, 0)
+    for ix in ixs:
+        for strip in (False, True):
+            want = format_cobs_text(recs, res, ix, strip_prefix=strip).encode()
+            assert format_cobs_text_fast(recs, res, ix, strip_prefix=strip, results_ptr=C.pointer(r)) == want
+    # merged
+    refs = {0: [f"SAM{d}" for d in range(n_docs)], 1: [], 2: [f"ERR{d}" for d in range(n_docs)]}
+    offs = np.zeros(nq + 1, np.uint64)
+    cands = []
+    for q in range(nq):
+        for _ in range(rnd.randrange(0, 5)):
+            b = rnd.choice([0, 2])
+            cands.append((rnd.randrange(1, 500), b, rnd.randrange(n_docs), 0))
+        offs[q + 1] = len(cands)
+    ca = np.array(cands, dtype=CAND_DT)
+    m = _lib.Merged(nq, C.cast(offs.ctypes.data, C.POINTER(C.c_uint64)), C.cast(ca.ctypes.data, C.POINTER(_lib.Cand)), 0)
+    qrecs = [(f"q{q}", "ACGT" * (q % 5)) for q in range(nq)]
+    assert format_filter_fasta_fast(qrecs, C.pointer(m), refs) == format_filter_fasta(qrecs, offs, ca, refs).encode()
