@@ -195,7 +195,7 @@ def cmd_match_db(a):
     n_shards, shard = 1, 0
     if a.shard:
         shard, n_shards = (int(x) for x in a.shard.split("/"))
-    budget = a.hbm_budget or 160 * 10 ** 9
+    budget = a.round_bytes or (int(a.hbm_budget * 0.9) if a.hbm_budget else 160 * 10 ** 9)
     plan = sharding.assign([shapes[b] for b in todo], n_shards, budget) if todo else sharding.Plan(n_shards)
     with Matcher(a.device, a.hbm_budget) as m:
         m.set_queries(records)
@@ -282,6 +282,9 @@ def build_parser():
                    help="process only the batches the LPT plan gives to GPU I of N (one process per GPU); "
                         "run `filter` over all match files afterwards")
     d.add_argument("--load-workers", type=int, default=8, help="concurrent xz decoders while loading")
+    d.add_argument("--round-bytes", type=int, default=0,
+                   help="HBM bytes of indexes resident at once (default 90%% of --hbm-budget, else 160e9); "
+                        "batches beyond it are streamed through in further rounds")
     d.add_argument("--device", type=int, default=0)
     d.set_defaults(fn=cmd_match_db)
     return ap

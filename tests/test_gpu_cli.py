@@ -98,3 +98,23 @@ def test_match_db_shards_cover_all_batches(tmp_path):
               str(batches), "-q", os.path.join(H.GOLDEN, "queries.fa"), "--match-dir", str(mdir),
               "-t", "0.7", "-n", "100", "--resume"])
     assert r.returncode == 0 and before == {f: os.path.getmtime(mdir / f) for f in os.listdir(mdir)}
+
+
+def test_match_db_streams_overflow_rounds(tmp_path):
+    """Indexes that do not fit together are streamed through HBM in rounds (load, match, write,
+    evict); the outputs do not depend on the round structure."""
+    batches = tmp_path / "batches.txt"
+    batches.write_text("\n".join(H.GOLDEN_BATCHES) + "\n")
+    mdir, out = tmp_path / "03_match", tmp_path / "q.fa"
+    r = _run([sys.executable, "-m", "phylign_b200.cli", "match-db", "--cobs-dir", H.GOLDEN, "--batches",
+              str(batches), "-q", os.path.join(H.GOLDEN, "queries.fa"), "--match-dir", str(mdir),
+              "--filter-out", str(out), "-t", "0.7", "-n", "1", "--round-bytes", "500000"])
+    assert r.returncode == 0, r.stderr
+    for b in H.GOLDEN_BATCHES:
+        assert gzip.open(mdir / f"{b}____queries.gz", "rt").read() == H.golden_match_text(b, 1)
+    assert out.read_text() == H.golden_filter_fa(1)
+    # a batch larger than the round budget is an error, not a silent skip
+    r = _run([sys.executable, "-m", "phylign_b200.cli", "match-db", "--cobs-dir", H.GOLDEN, "--batches",
+              str(batches), "-q", os.path.join(H.GOLDEN, "queries.fa"), "--match-dir", str(tmp_path / "y"),
+              "--round-bytes", "1000"])
+    assert r.returncode != 0 and "budget" in r.stderr

@@ -210,3 +210,27 @@ def test_c_formatters_equal_python_formatters():
     m = _lib.Merged(nq, C.cast(offs.ctypes.data, C.POINTER(C.c_uint64)), C.cast(ca.ctypes.data, C.POINTER(_lib.Cand)), 0)
     qrecs = [(f"q{q}", "ACGT" * (q % 5)) for q in range(nq)]
     assert format_filter_fasta_fast(qrecs, C.pointer(m), refs) == format_filter_fasta(qrecs, offs, ca, refs).encode()
+
+
+def test_fast_modulo_algorithm_is_exact():
+    """The multiply-high modulo of csrc/phy_internal.cuh (phy_fastmod), restated with Python
+    integers: exact for every 64-bit hash and every signature_size < 2^32."""
+    import random
+    rnd = random.Random(9)
+    M64 = (1 << 64) - 1
+
+    def fastmod(n, d):
+        magic = M64 // d                       # host side: UINT64_MAX / signature_size
+        q = (n * magic) >> 64                  # __umul64hi
+        r = (n - q * d) & M64
+        if r >= d:
+            r -= d
+        return r
+
+    ds = [1, 2, 3, 7, 97, 128, 4096, 65536, 1 << 31, (1 << 32) - 2, (1 << 32) - 5, 21188834, 2803644, 31_800_000]
+    ds += [rnd.randrange(1, (1 << 32) - 1) for _ in range(300)]
+    ns = [0, 1, M64, M64 - 1, 1 << 63, (1 << 63) - 1, 1 << 32, (1 << 32) - 1]
+    for d in ds:
+        for n in ns + [rnd.randrange(1 << 64) for _ in range(200)] + [d - 1, d, d + 1, 2 * d - 1, 2 * d, M64 // d * d]:
+            n &= M64
+            assert fastmod(n, d) == n % d, (n, d)
