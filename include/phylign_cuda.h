@@ -66,6 +66,9 @@ int phy_index_evict(phy_ctx* ctx, int idx_id);
 int phy_index_set_ranks(phy_ctx* ctx, int idx_id, uint32_t batch_rank,
                         const uint32_t* ref_rank);
 
+/* a resident index can be left out of phy_match_run without evicting it (default: active) */
+int phy_index_set_active(phy_ctx* ctx, int idx_id, int active);
+
 typedef struct phy_index_info {
     uint64_t signature_size, num_hashes, hbm_bytes;
     uint32_t term_size, n_docs, row_size, row_stride, batch_rank;

@@ -79,6 +79,7 @@ PROTOTYPES = {
     "phy_index_commit": (C.c_int, [_P, C.c_int]),
     "phy_index_evict": (C.c_int, [_P, C.c_int]),
     "phy_index_set_ranks": (C.c_int, [_P, C.c_int, C.c_uint32, C.c_void_p]),
+    "phy_index_set_active": (C.c_int, [_P, C.c_int, C.c_int]),
     "phy_index_info_get": (C.c_int, [_P, C.c_int, C.POINTER(IndexInfo)]),
     "phy_index_count": (C.c_int, [_P, C.POINTER(C.c_int)]),
     "phy_index_download": (C.c_int, [_P, C.c_int, C.c_void_p, C.c_uint64]),

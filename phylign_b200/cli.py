@@ -59,6 +59,17 @@ def _postprocess_stream(fin, fout, keep: int):
 
 # ------------------------------------------------------------------------------------ cobs query
 def cmd_cobs_query(a):
+    server = getattr(a, "server", None) or os.environ.get("PHYLIGN_SERVER")
+    if server:      # resident indexes: ship the request to `phylign_b200.cli serve`
+        from .server import request
+        head, payload = request(server, {"cmd": "query", "index": os.path.abspath(a.i), "query": os.path.abspath(a.f),
+                                         "threshold": a.t, "top_n": a.top_n, "floor": a.floor,
+                                         "index_sizes": a.index_sizes})
+        if not head.get("ok"):
+            _die(head.get("error", "server error"))
+        sys.stdout.buffer.write(payload)
+        sys.stdout.buffer.flush()
+        return
     from .matcher import Matcher
     records = fasta.read_cobs_records(a.f)
     with Matcher(a.device) as m:
@@ -237,6 +248,7 @@ def build_parser():
     q.add_argument("--top-n", type=int, default=0, help="fuse postprocess_cobs.py -n N (names get the '_acc' form)")
     q.add_argument("--floor", action="store_true", help="threshold = floor(t*K) instead of ceil (SURVEY A.6)")
     q.add_argument("--device", type=int, default=0)
+    q.add_argument("--server", default=None, help="socket of a resident `serve` process (or $PHYLIGN_SERVER)")
     q.set_defaults(fn=cmd_cobs_query)
 
     r = sub.add_parser("run-cobs-streaming")
@@ -249,6 +261,14 @@ def build_parser():
     r.set_defaults(fn=lambda a: cmd_cobs_query(argparse.Namespace(
         t=a.kmer_thres, T=0, i=a.cobs_index_xz, index_sizes=a.uncompressed_size, f=a.query, top_n=0,
         floor=False, device=a.device)))
+
+    sv = sub.add_parser("serve", help="keep indexes resident in HBM and answer `cobs query --server` requests")
+    sv.add_argument("--socket", required=True)
+    sv.add_argument("--device", type=int, default=0)
+    sv.add_argument("--hbm-budget", type=int, default=0)
+    sv.add_argument("--preload", nargs="*", default=[], help="index files to load before serving")
+    sv.set_defaults(fn=lambda a: __import__("phylign_b200.server", fromlist=["serve"]).serve(
+        a.socket, a.device, a.hbm_budget, a.preload))
 
     p = sub.add_parser("postprocess")
     p.add_argument("-n", dest="keep", required=True, type=int, metavar="int", help="no. of best hits to keep")

@@ -415,6 +415,14 @@ extern "C" int phy_index_set_ranks(phy_ctx* ctx, int idx_id, uint32_t batch_rank
     return PHY_OK;
 }
 
+extern "C" int phy_index_set_active(phy_ctx* ctx, int idx_id, int active) {
+    HostIndex* ix = get_index(ctx, idx_id);
+    if (!ix) return PHY_ERR_ARG;
+    ix->active = active != 0;
+    ctx->have_match = ctx->have_merged = false;
+    return PHY_OK;
+}
+
 extern "C" int phy_index_info_get(phy_ctx* ctx, int idx_id, phy_index_info* out) {
     HostIndex* ix = get_index(ctx, idx_id);
     if (!ix || !out) return PHY_ERR_ARG;
@@ -530,7 +538,7 @@ static int resident_shape(phy_ctx* ctx, uint32_t* k, uint32_t* canon, uint32_t* 
     for (size_t i = 0; i < ctx->idx.size(); i++) {
         const HostIndex& ix = ctx->idx[i];
         if (!ix.alive || !ix.committed) continue;
-        if (only_idx >= 0 && (int)i != only_idx) continue;
+        if (only_idx >= 0 ? (int)i != only_idx : !ix.active) continue;
         if (first) { *k = ix.term_size; *canon = ix.canon; first = false; }
         else if (*k != ix.term_size || *canon != ix.canon) {
             phy_set_error(ctx, "resident indexes disagree on term_size/canonicalize (cobs requires them equal)");
@@ -539,7 +547,7 @@ static int resident_shape(phy_ctx* ctx, uint32_t* k, uint32_t* canon, uint32_t* 
         *nh = std::max(*nh, ix.d.num_hashes);
     }
     if (first) {
-        phy_set_error(ctx, "no committed index resident");
+        phy_set_error(ctx, "no committed (and active) index resident");
         return PHY_ERR_STATE;
     }
     return PHY_OK;

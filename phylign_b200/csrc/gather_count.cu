@@ -1040,7 +1040,7 @@ int phy_launch_gather(phy_ctx* ctx, const phy_match_params* p) {
     std::vector<uint32_t> cls[6], wide;  // lpr 1,2,4,8,16,32 ; wide = stride > 512 (general path)
     for (size_t i = 0; i < ctx->idx.size(); i++) {
         const HostIndex& ix = ctx->idx[i];
-        if (!ix.alive || !ix.committed) continue;
+        if (!ix.alive || !ix.committed || !ix.active) continue;
         if (ix.d.stride > PHY_CHUNK_BYTES) { wide.push_back((uint32_t)i); continue; }
         int c = 0;
         while ((1 << c) < ix.lpr) c++;
@@ -1142,7 +1142,7 @@ int phy_launch_gather(phy_ctx* ctx, const phy_match_params* p) {
         // general path: long queries against every index; every query against wide indexes
         for (size_t i = 0; i < ctx->idx.size(); i++) {
             const HostIndex& ix = ctx->idx[i];
-            if (!ix.alive || !ix.committed) continue;
+            if (!ix.alive || !ix.committed || !ix.active) continue;
             const bool is_wide = ix.d.stride > PHY_CHUNK_BYTES;
             std::vector<uint32_t> qs = slowq;
             if (is_wide) qs.insert(qs.end(), fastq.begin(), fastq.end());

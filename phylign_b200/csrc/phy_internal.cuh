@@ -47,7 +47,7 @@ struct HostIndex {
     std::string name;
     uint32_t term_size = 31;
     uint8_t canon = 1;
-    bool alive = false, committed = false;
+    bool alive = false, committed = false, active = true;  // active: takes part in phy_match_run
     uint64_t pushed = 0, body_bytes = 0, hbm_bytes = 0;
     uint8_t* rows_mut = nullptr;
     uint32_t* ref_rank_mut = nullptr;

@@ -313,9 +313,21 @@ class Matcher:
         nk = np.frombuffer(C.string_at(r.n_kmers, nq * 4), dtype=np.uint32) if nq else np.zeros(0, np.uint32)
         return MatchResult(units, hits, nk, nq, int(r.h2d_bytes), int(r.d2h_bytes), owner)
 
-    def match(self, threshold: float, top_n: int = 0, floor_mode: bool = False, merge_top_n: int = 0):
-        self.match_run(threshold, top_n, floor_mode, merge_top_n)
-        return self.fetch()
+    def match(self, threshold: float, top_n: int = 0, floor_mode: bool = False, merge_top_n: int = 0,
+              only=None):
+        """Run + fetch.  `only`: index ids to query (the other resident indexes sit this one out)."""
+        if only is None:
+            self.match_run(threshold, top_n, floor_mode, merge_top_n)
+            return self.fetch()
+        only = set(only)
+        try:
+            for i in self.indexes:
+                self._ck(self._L.phy_index_set_active(self._ctx, i, int(i in only)))
+            self.match_run(threshold, top_n, floor_mode, merge_top_n)
+            return self.fetch()
+        finally:
+            for i in self.indexes:
+                self._L.phy_index_set_active(self._ctx, i, 1)
 
     def merged(self):
         """(offs[nq+1], cands structured array) of the cross-index top-N + ties merge.

@@ -118,3 +118,40 @@ def test_match_db_streams_overflow_rounds(tmp_path):
               str(batches), "-q", os.path.join(H.GOLDEN, "queries.fa"), "--match-dir", str(tmp_path / "y"),
               "--round-bytes", "1000"])
     assert r.returncode != 0 and "budget" in r.stderr
+
+
+def test_resident_server_answers_cobs_queries(tmp_path):
+    """`serve` keeps indexes in HBM; `cobs query --server` prints the same bytes as a cold run."""
+    import time
+    from phylign_b200.server import request
+    sock = str(tmp_path / "phy.sock")
+    srv = subprocess.Popen([sys.executable, "-m", "phylign_b200.cli", "serve", "--socket", sock,
+                            "--preload", os.path.join(H.GOLDEN, "aaa__01.cobs_classic.xz")],
+                           env=ENV, cwd=ROOT, stderr=subprocess.PIPE, text=True)
+    try:
+        for _ in range(600):
+            if os.path.exists(sock):
+                break
+            assert srv.poll() is None, srv.stderr.read()
+            time.sleep(0.1)
+        for rep in range(2):
+            for b in H.GOLDEN_BATCHES:
+                r = _run([f"{ROOT}/scripts/cobs", "query", "-t", "0.7", "-T", "4", "-i",
+                          os.path.join(H.GOLDEN, f"{b}.cobs_classic.xz"), "-f", f"{H.GOLDEN}/queries.fa",
+                          "--server", sock])
+                assert r.returncode == 0, r.stderr
+                assert r.stdout == H.golden_cobs_text(b), (rep, b)
+        head, _ = request(sock, {"cmd": "status"})
+        assert head["ok"] and head["loads"] == 3 and head["hits"] == 4 and head["queries"] == 6
+        r = _run([f"{ROOT}/scripts/cobs", "query", "-t", "0.7", "-i", "/nonexistent.cobs_classic",
+                  "-f", f"{H.GOLDEN}/queries.fa", "--server", sock])
+        assert r.returncode != 0 and "error" in r.stderr
+    finally:
+        try:
+            request(sock, {"cmd": "shutdown"}, timeout=30)
+        except Exception:
+            pass
+        try:
+            srv.wait(timeout=30)
+        except Exception:
+            srv.kill()
