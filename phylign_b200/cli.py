@@ -29,7 +29,6 @@ import sys
 import numpy as np
 
 from . import fasta
-from .cobs_index import ref_of
 from .cobs_text import format_cobs_text_fast, format_filter_fasta_fast
 
 

@@ -10,7 +10,6 @@ import numpy as np
 import pytest
 
 import oracle
-from oracle import filters
 from tests import helpers as H
 
 pytestmark = pytest.mark.gpu
