@@ -186,6 +186,12 @@ int phy_sync(phy_ctx* ctx);
 /* per-phase device times (ms) of the last phy_match_run:
  * [0] hash  [1] gather+count(+select)  [2] sort/merge  [3] launches of own kernels */
 int phy_last_phase_ms(phy_ctx* ctx, float out[4]);
+/* index-row bytes (file row size, not stride) the fused ring kernel really gathered in the last
+ * phy_match_run: < sum K*row_size when threshold pruning ended units early */
+int phy_last_gather_bytes(phy_ctx* ctx, uint64_t* bytes);
+/* tuning / A-B switches: "prune" 0|1 (exact threshold pruning, default 1),
+ * "kernel_path" 1|2|3 (register-staged | bulk-copy ring | cp.async ring, default 3) */
+int phy_ctx_set_option(phy_ctx* ctx, const char* name, int64_t value);
 /* write a buffer larger than L2 (bench hygiene between timed iterations) */
 int phy_flush_l2(phy_ctx* ctx);
 

@@ -106,6 +106,8 @@ PROTOTYPES = {
     "phy_timer_stop": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "phy_sync": (C.c_int, [_P]),
     "phy_last_phase_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
+    "phy_last_gather_bytes": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    "phy_ctx_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
     "phy_flush_l2": (C.c_int, [_P]),
     "phy_index_synth": (C.c_int, [_P, C.c_int, C.POINTER(SynthSpec)]),
     "phy_index_insert": (C.c_int, [_P, C.c_int, C.c_void_p]),

@@ -83,6 +83,7 @@ extern "C" int phy_ctx_create(phy_ctx** out, int device, uint64_t hbm_budget) {
     ctx->device = device;
     ctx->n_sm = prop.multiProcessorCount;
     if (getenv("PHY_KERNEL_PATH")) ctx->kernel_path = atoi(getenv("PHY_KERNEL_PATH"));
+    if (getenv("PHY_NO_PRUNE") && atoi(getenv("PHY_NO_PRUNE"))) ctx->prune = false;
     PHY_CUDA(ctx, cudaSetDevice(device));
     size_t fr = 0, tot = 0;
     PHY_CUDA(ctx, cudaMemGetInfo(&fr, &tot));
@@ -757,6 +758,21 @@ extern "C" int phy_sync(phy_ctx* ctx) {
 extern "C" int phy_last_phase_ms(phy_ctx* ctx, float out[4]) {
     if (!ctx || !out) return PHY_ERR_ARG;
     for (int i = 0; i < 4; i++) out[i] = ctx->phase_ms[i];
+    return PHY_OK;
+}
+extern "C" int phy_last_gather_bytes(phy_ctx* ctx, uint64_t* bytes) {
+    if (!ctx || !bytes) return PHY_ERR_ARG;
+    *bytes = ctx->gathered_bytes;
+    return PHY_OK;
+}
+extern "C" int phy_ctx_set_option(phy_ctx* ctx, const char* name, int64_t value) {
+    if (!ctx || !name) return PHY_ERR_ARG;
+    if (!strcmp(name, "prune")) ctx->prune = value != 0;
+    else if (!strcmp(name, "kernel_path") && value >= 1 && value <= 3) ctx->kernel_path = (int)value;
+    else {
+        phy_set_error(ctx, "unknown option %s=%lld", name, (long long)value);
+        return PHY_ERR_ARG;
+    }
     return PHY_OK;
 }
 extern "C" int phy_flush_l2(phy_ctx* ctx) {

@@ -187,6 +187,7 @@ struct GatherArgs {
     uint32_t* unit_flag;  // [index slot][query] 0/1 (null: host orders the units)
     uint32_t* unit_id;    // [index slot][query] position in units[]
     uint32_t nq;
+    uint32_t prune;       // threshold pruning on (ring kernel)
 };
 
 // Threshold (cobs counts_to_result), top-N + ties (postprocess_cobs.py:21-38) and emission of
@@ -529,16 +530,25 @@ constexpr int RING_NB = PHY_RING_NB, RING_WARPS = PHY_RING_WARPS;
 
 // One unit per group of LPR lanes: add the rows of its `nrows` k-mers (hashes at hq) into pl.
 // `nmax` = largest nrows among the groups of the warp (all lanes run the same trip count).
+// THRESHOLD PRUNING (exact): after x of the K rows a document with count c can still reach
+// the threshold T only if c + (K - x) >= T.  At every 4th batch (where the carry-save tree
+// has no pending partial sums, so the planes ARE the counts) a lane whose 128 documents are
+// all out of reach stops fetching its 16 B, and a unit whose documents are all out of reach
+// ends.  Documents that can still pass keep being counted to the end, so n_pass, the kept
+// set and every reported score are unchanged; only rows that cannot change the output are
+// skipped.  With cobs_kmer_thres 0.7 and a 0.3 false-positive rate an unrelated batch dies
+// after ~half of a read's k-mers.  prune_T = 0 switches it off (phy_scores, general path).
 template <int LPR, int P, int NB>
-__device__ __forceinline__ void ring_accumulate(uint32_t (&pl)[P][4], uint32_t ring, const uint8_t* colbase,
+__device__ __forceinline__ uint32_t ring_accumulate(uint32_t (&pl)[P][4], uint32_t ring, const uint8_t* colbase,
                                                 bool lane_on, uint32_t stride, uint64_t sig, uint64_t magic,
                                                 const uint64_t* __restrict__ hq, uint32_t nrows, uint32_t nmax,
-                                                int lane) {
+                                                int lane, uint32_t prune_T, unsigned gm) {
     constexpr int HB = LPR >= 8 ? LPR : 8;  // rows whose hashes are fetched per block
     constexpr int NH = HB / LPR;            // hashes per lane per block
     constexpr int BPH = HB / 8;             // batches per hash block
     const int col = lane & (LPR - 1), gbase = lane - col;
-    const uint32_t nb = (nmax + 7) >> 3;    // warp-uniform number of batches
+    uint32_t nb = (nmax + 7) >> 3;          // warp-uniform number of batches (shrinks when units die)
+    const uint32_t K = nrows;               // this unit's k-mer count (nrows itself shrinks on early exit)
     uint32_t p8[4] = {0, 0, 0, 0}, p16[4] = {0, 0, 0, 0};
     uint32_t myrow[NH];
     uint64_t hnext[NH];
@@ -566,15 +576,19 @@ __device__ __forceinline__ void ring_accumulate(uint32_t (&pl)[P][4], uint32_t r
                 const int src = LPR >= 8 ? gbase + (int)s * 8 + r : gbase + (r % LPR);
                 const int slot = LPR >= 8 ? 0 : r / LPR;
                 const uint32_t rr = __shfl_sync(FULL, myrow[slot], src);
-                if (rr != PHY_ROW_INVALID && lane_on) cp_async16(dst + r * 512, colbase + (uint64_t)rr * stride);
+                if (rr != PHY_ROW_INVALID && j * 8 + r < nrows && lane_on)
+                    cp_async16(dst + r * 512, colbase + (uint64_t)rr * stride);
             }
         }
         cp_async_commit();  // (possibly empty) group: keeps the wait_group distance constant
     };
 #pragma unroll 1
     for (uint32_t j = 0; j < (uint32_t)NB; j++) issue(j);
+    // warp-uniform switch: the checkpoint below holds warp-wide votes, so every lane must take it
+    const bool prune_any = __any_sync(FULL, prune_T != 0);
+    uint32_t j = 0;
 #pragma unroll 1
-    for (uint32_t j = 0; j < nb; j++) {
+    for (; j < nb; j++) {
         cp_async_wait<NB - 1>();  // batch j has landed (this lane's own 16-B pieces)
         const uint32_t src = ring + (j % NB) * BULK_BATCH_BYTES;
         uint4 v[8];
@@ -584,10 +598,31 @@ __device__ __forceinline__ void ring_accumulate(uint32_t (&pl)[P][4], uint32_t r
             else v[r] = make_uint4(0, 0, 0, 0);
         }
         csa_batch3<P>(pl, v, j, p8, p16);
+        if (prune_any && ((j + 1) & 3u) == 0) {  // planes are exact counts here
+            const uint32_t x = min((j + 1) * 8u, nrows);  // rows of this unit counted so far
+            bool alive = lane_on;
+            if (lane_on && prune_T != 0 && prune_T + x > K) {  // need = T - (K - x) more than zero
+                const uint32_t need = prune_T + x - K;
+                uint32_t any = 0;
+#pragma unroll
+                for (int w = 0; w < 4; w++) any |= ge_mask<P>(pl, w, need);
+                alive = any != 0;
+                lane_on = alive;                      // my 128 documents cannot pass any more
+            }
+            const unsigned live = __ballot_sync(FULL, alive && x < nrows);
+            if ((live & gm) == 0 && x < nrows) nrows = x;  // the whole unit is decided: stop here
+            if (live != FULL) {                       // some unit ended: the warp may finish earlier
+                uint32_t m = (nrows + 7) >> 3;
+#pragma unroll
+                for (int o = 16; o >= LPR; o >>= 1) m = max(m, __shfl_xor_sync(FULL, m, o));
+                nb = max(m, j + 1);
+            }
+        }
         issue(j + NB);  // refill the slot: its values were consumed above by this very lane
     }
     cp_async_wait<0>();
-    csa_flush3<P>(pl, nb, p8, p16);
+    csa_flush3<P>(pl, j, p8, p16);
+    return min(j * 8u, K);  // rows of this unit that were fetched and counted
 }
 
 template <int LPR, int P, int NB, int WARPS>
@@ -630,8 +665,11 @@ __global__ void __launch_bounds__(WARPS * 32) gather_count_ring_kernel(const Gat
         uint32_t pl[P][4];
 #pragma unroll
         for (int p = 0; p < P; p++) pl[p][0] = pl[p][1] = pl[p][2] = pl[p][3] = 0;
-        ring_accumulate<LPR, P, NB>(pl, ring, colbase, (uint32_t)col * 16u < stride, stride, sig, magic, hq, nrows,
-                                    nmax, lane);
+        const uint32_t prune_T = (a.prune && live) ? a.T[q] : 0u;
+        const uint32_t done = ring_accumulate<LPR, P, NB>(pl, ring, colbase, (uint32_t)col * 16u < stride, stride,
+                                                          sig, magic, hq, nrows, nmax, lane, prune_T, gm);
+        if (live && col == 0)  // bytes of index rows this unit really gathered (pruning makes it < K rows)
+            atomicAdd(&a.counters[5], (unsigned long long)done * ((n_docs + 7u) >> 3));
         if (live) select_and_emit<LPR, P>(pl, a, q, idx_id, n_docs, nrows, lane, gm);
         __syncwarp();
     }
@@ -678,7 +716,8 @@ __global__ void __launch_bounds__(WARPS * 32) accum_scores_ring_kernel(
 #pragma unroll
         for (int p = 0; p < P; p++) pl[p][0] = pl[p][1] = pl[p][2] = pl[p][3] = 0;
         ring_accumulate<LPR, P, NB>(pl, ring, ix.rows + byte0, live && byte0 < stride, stride, ix.sig, ix.magic,
-                                    hashes + (live ? koffs[it.query] + it.k0 : 0), nrows, nmax, lane);
+                                    hashes + (live ? koffs[it.query] + it.k0 : 0), nrows, nmax, lane, 0u,
+                                    group_mask<LPR>(lane));
         if (live) {
             uint32_t* row = scores + (uint64_t)it.slot * n_docs;
 #pragma unroll
@@ -1066,6 +1105,7 @@ int phy_launch_gather(phy_ctx* ctx, const phy_match_params* p) {
         PHY_TRY(phy_ensure(ctx, ctx->d_units, units_cap));
         PHY_TRY(phy_ensure(ctx, ctx->d_hits, hits_cap));
         PHY_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, 2 * sizeof(unsigned long long), ctx->stream));
+        PHY_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p + 5, 0, sizeof(unsigned long long), ctx->stream));
         PHY_CUDA(ctx, cudaMemsetAsync(ctx->d_qcount.p, 0, (ctx->nq + 1) * sizeof(uint32_t), ctx->stream));
         GatherArgs a;
         a.indexes = ctx->d_indexes.p;
@@ -1073,6 +1113,7 @@ int phy_launch_gather(phy_ctx* ctx, const phy_match_params* p) {
         a.koffs = ctx->d_koffs.p; a.nk = ctx->d_nk.p; a.T = ctx->d_T.p;
         a.hashes = ctx->d_hashes.p; a.total_kmers = ctx->total_kmers;
         a.top_n = p->top_n;
+        a.prune = ctx->prune ? 1u : 0u;
         a.units = ctx->d_units.p; a.units_cap = ctx->d_units.cap;
         a.hits = ctx->d_hits.p; a.hits_cap = ctx->d_hits.cap;
         a.counters = ctx->d_counters.p; a.qcount = ctx->d_qcount.p;
@@ -1163,9 +1204,10 @@ int phy_launch_gather(phy_ctx* ctx, const phy_match_params* p) {
                 PHY_CUDA(ctx, cudaGetLastError());
             }
         }
-        unsigned long long cnt[2];
+        unsigned long long cnt[6];
         PHY_CUDA(ctx, cudaMemcpyAsync(cnt, ctx->d_counters.p, sizeof cnt, cudaMemcpyDeviceToHost, ctx->stream));
         PHY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->gathered_bytes = cnt[5];
         if (cnt[0] <= ctx->d_hits.cap && cnt[1] <= ctx->d_units.cap) {
             ctx->n_hits = cnt[0];
             ctx->n_units = cnt[1];

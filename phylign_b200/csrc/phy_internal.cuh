@@ -56,6 +56,7 @@ struct HostIndex {
 
 struct phy_ctx {
     int device = 0, n_sm = 148;
+    bool prune = true;    // PHY_NO_PRUNE=1 switches the exact threshold pruning of the ring kernel off
     int kernel_path = 3;  // PHY_KERNEL_PATH: 1 = register-staged (A), 2 = bulk-copy ring (B), 3 = cp.async ring (C)
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_ph[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -103,7 +104,7 @@ struct phy_ctx {
     uint64_t n_final = 0;
     uint32_t merge_top_n = 0;
 
-    uint64_t h2d_bytes = 0, launches = 0;
+    uint64_t h2d_bytes = 0, launches = 0, gathered_bytes = 0;
     float phase_ms[4] = {0, 0, 0, 0};
     DevBuf<uint8_t> d_flush;
 

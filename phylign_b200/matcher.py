@@ -372,6 +372,14 @@ class Matcher:
     def flush_l2(self):
         self._ck(self._L.phy_flush_l2(self._ctx))
 
+    def gathered_bytes(self) -> int:
+        b = C.c_uint64()
+        self._ck(self._L.phy_last_gather_bytes(self._ctx, C.byref(b)))
+        return b.value
+
+    def set_option(self, name: str, value: int):
+        self._ck(self._L.phy_ctx_set_option(self._ctx, name.encode(), int(value)))
+
     def phase_ms(self):
         a = (C.c_float * 4)()
         self._ck(self._L.phy_last_phase_ms(self._ctx, a))
