@@ -352,7 +352,7 @@ def run_ours(args, w, rank, world, local_rank):
     traffic = None
     try:   # DRAM bytes per launch from the committed ncu capture of this exact workload, else null
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        key = f"{kernel}|{w['name']}|{w['n_reads']}|{w['read_len']}|{w['n_indexes']}|{w['n_docs']}|{world}"
+        key = f"{kernel}|{w['name']}|{w['n_reads']}|{w['read_len']}|{w['n_indexes']}|{w['n_docs']}|{world}|prune1"
         traffic = tj[key]["traffic_bytes"] if key in tj else None
     except Exception:
         pass
