@@ -317,3 +317,41 @@ def test_deterministic_output(M, golden_queries):
                  hits[int(u["offset"]):int(u["offset"]) + int(u["n_kept"])].tobytes()) for u in units]
     assert canon(runs[0]) == canon(runs[1]) == canon(runs[2])
     assert runs[0][2:] == runs[1][2:] == runs[2][2:]
+
+
+def test_c_abi_state_and_argument_errors(M):
+    """Misuse of the C ABI returns a status and a message, never crashes or guesses."""
+    import ctypes as C
+    from phylign_b200 import _lib
+    L = _lib.load()
+    _evict_all(M)
+    ctx = M._ctx
+    rp = C.POINTER(_lib.Results)()
+    mp = C.POINTER(_lib.Merged)()
+    idx = C.c_int()
+    assert L.phy_index_begin(ctx, b"x__01", 32, 1, 100, 1, 8, C.byref(idx)) == -2          # k > 31
+    assert L.phy_index_begin(ctx, b"x__01", 31, 1, 0, 1, 8, C.byref(idx)) == -2           # empty signature
+    assert L.phy_index_begin(ctx, b"x__01", 31, 1, 1 << 32, 1, 8, C.byref(idx)) == -2     # >= 2^32 rows
+    assert L.phy_index_begin(ctx, b"x__01", 31, 1, 100, 1, (1 << 20) + 1, C.byref(idx)) == -2
+    assert L.phy_index_begin(ctx, b"x__01", 31, 1, 100, 1, 8, C.byref(idx)) == 0
+    i = idx.value
+    buf = (C.c_char * 100)()
+    assert L.phy_index_commit(ctx, i) == -4                                               # nothing pushed yet
+    assert b"expected" in L.phy_last_error(ctx)
+    assert L.phy_index_push(ctx, i, buf, 60) == 0 and L.phy_index_push(ctx, i, buf, 41) == -4   # 101 > 100 bytes
+    assert L.phy_index_push(ctx, i, buf, 40) == 0 and L.phy_index_commit(ctx, i) == 0
+    assert L.phy_index_push(ctx, i, buf, 1) == -4                                         # after commit
+    assert L.phy_index_set_ranks(ctx, i, 4096, None) == -2
+    assert L.phy_index_commit(ctx, 99) == -2 and L.phy_index_evict(ctx, -1) == -2
+    M.set_queries([("q", "ACGT" * 10)])
+    assert L.phy_results_fetch(ctx, C.byref(rp)) == -4                                    # no match run yet
+    p = _lib.MatchParams(-0.1, 0, 0)
+    assert L.phy_match_run(ctx, C.byref(p), 0) == -2                                      # negative threshold
+    p = _lib.MatchParams(0.7, 0, 0)
+    assert L.phy_match_run(ctx, C.byref(p), 0) == 0
+    assert L.phy_merged_fetch(ctx, C.byref(mp)) == -4                                     # merge was not requested
+    assert L.phy_results_fetch(ctx, C.byref(rp)) == 0 and rp.contents.n_units == 0
+    L.phy_results_free(rp)
+    assert L.phy_ctx_set_option(ctx, b"nonsense", 1) == -2
+    assert L.phy_index_evict(ctx, i) == 0 and L.phy_index_evict(ctx, i) == -2
+    assert L.phy_ctx_create(C.byref(C.c_void_p()), 4096, 0) == -2                         # no such device
