@@ -29,6 +29,7 @@ import sys
 import numpy as np
 
 from . import fasta
+from .cobs_index import ref_of as _ref_of
 from .cobs_text import format_cobs_text_fast, format_filter_fasta_fast
 
 
@@ -107,37 +108,58 @@ def parse_match_file(path):
     return blocks
 
 
-def merge_match_files(m, query_fn, match_fns, keep: int, log=sys.stderr) -> str:
-    """filter_queries.py process_files on the GPU (phy_merge_host)."""
-    from .matcher import CAND_DT
+def _load_filter_queries(query_fn):
+    """(ordered {qname: seq}, {qname: position}) the way filter_queries.py:163-176 builds its dict."""
     queries = {}
     for qname, seq in fasta.read_fastx(query_fn):
         queries[qname] = seq                      # duplicate names overwrite, first position kept
-    qid = {q: i for i, q in enumerate(queries)}
-    per_batch = []
+    return queries, {q: i for i, q in enumerate(queries)}
+
+
+def _parsed_pieces(match_fns, qid, brank, log):
+    """Candidates of already written match files: [(qid array, CAND array)], {batch_rank: refs}."""
+    from .matcher import CAND_DT
+    pieces, refs_by_rank = [], {}
+    by_batch = {}
     for fn in match_fns:
         batch = os.path.basename(fn).split("____")[0]
         print(f"Translating matches {fn}", file=log)
-        per_batch.append((batch, parse_match_file(fn)))
-    batch_names = sorted({b for b, _ in per_batch})
-    brank = {b: i for i, b in enumerate(batch_names)}
-    refs_sorted = {b: sorted({ref for bb, blocks in per_batch if bb == b for _, hits in blocks for ref, _ in hits})
-                   for b in batch_names}
-    rrank = {b: {r: i for i, r in enumerate(refs_sorted[b])} for b in batch_names}
-    rows = [[] for _ in queries]
-    for batch, blocks in per_batch:
-        br, rr = brank[batch], rrank[batch]
+        by_batch.setdefault(batch, []).extend(parse_match_file(fn))
+    for batch, blocks in by_batch.items():
+        refs = sorted({ref for _, hits in blocks for ref, _ in hits})
+        rr = {r: i for i, r in enumerate(refs)}
+        br = brank[batch]
+        refs_by_rank[br] = refs
+        qs, rows = [], []
         for qname, hits in blocks:
             if qname not in qid:
-                raise KeyError(f"query {qname!r} of batch {batch} is not in {query_fn}")
-            rows[qid[qname]].extend((k, br, rr[ref], rr[ref]) for ref, k in hits)
-    offs = np.zeros(len(rows) + 1, dtype=np.uint64)
-    offs[1:] = np.cumsum([len(r) for r in rows], dtype=np.uint64)
-    flat = [t for r in rows for t in r]
-    cands = np.array(flat, dtype=CAND_DT) if flat else np.zeros(0, CAND_DT)
-    moffs, mc = m.merge_host(offs, cands, keep)
-    refs_by_rank = {brank[b]: refs_sorted[b] for b in batch_names}
+                raise KeyError(f"query {qname!r} of batch {batch} is not in the query file")
+            qs.extend([qid[qname]] * len(hits))
+            rows.extend((k, br, rr[ref], rr[ref]) for ref, k in hits)
+        pieces.append((np.array(qs, dtype=np.int64), np.array(rows, dtype=CAND_DT) if rows else np.zeros(0, CAND_DT)))
+    return pieces, refs_by_rank
+
+
+def _final_merge(m, queries, pieces, refs_by_rank, keep: int) -> str:
+    """Global top-N + ties over candidate pieces (filter_queries.py:123-150) on the GPU."""
+    from .matcher import CAND_DT
+    nq = len(queries)
+    qs = np.concatenate([p[0] for p in pieces]) if pieces else np.zeros(0, np.int64)
+    cs = np.concatenate([p[1] for p in pieces]) if pieces else np.zeros(0, CAND_DT)
+    order = np.argsort(qs, kind="stable")
+    offs = np.zeros(nq + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum(np.bincount(qs, minlength=nq), dtype=np.uint64)
+    m.merge_host(offs, cs[order], keep)
     return format_filter_fasta_fast(list(queries.items()), m._merged_owner.ptr, refs_by_rank).decode()
+
+
+def merge_match_files(m, query_fn, match_fns, keep: int, log=sys.stderr) -> str:
+    """filter_queries.py process_files on the GPU (phy_merge_host)."""
+    queries, qid = _load_filter_queries(query_fn)
+    batch_names = sorted({os.path.basename(fn).split("____")[0] for fn in match_fns})
+    brank = {b: i for i, b in enumerate(batch_names)}
+    pieces, refs_by_rank = _parsed_pieces(match_fns, qid, brank, log)
+    return _final_merge(m, queries, pieces, refs_by_rank, keep)
 
 
 def cmd_filter(a):
@@ -207,25 +229,42 @@ def cmd_match_db(a):
         shard, n_shards = (int(x) for x in a.shard.split("/"))
     budget = a.round_bytes or (int(a.hbm_budget * 0.9) if a.hbm_budget else 160 * 10 ** 9)
     plan = sharding.assign([shapes[b] for b in todo], n_shards, budget) if todo else sharding.Plan(n_shards)
+    # 04_filter is merged from the device results of every round (no re-parsing of what was just
+    # written); only match files that already existed (--resume) are parsed
+    want_filter = bool(a.filter_out) and n_shards == 1
+    if a.filter_out and n_shards != 1:
+        _die("--filter-out needs all batches: run `filter` over the match files of all shards instead")
+    queries, qid = _load_filter_queries(a.q) if want_filter else ({}, {})
+    brank = sharding.global_batch_ranks(batches)
+    rec2qid = np.array([qid[h.split(" ")[0]] for h, _ in records], dtype=np.int64) if want_filter else None
+    pieces, refs_by_rank = [], {}
+    if want_filter and merged_inputs:
+        pieces, refs_by_rank = _parsed_pieces(merged_inputs, qid, brank, open(os.devnull, "w"))
     with Matcher(a.device, a.hbm_budget) as m:
-        m.set_queries(records)
         for rnd in plan.rounds:                               # resident round: load, match, write, evict
             mine = sorted(x.name for x in rnd[shard])
             if not mine:
                 continue
             loaded = m.load_indexes([path_of(b) for b in mine], mine, workers=a.load_workers)
-            res = m.match(a.t, top_n=a.n, floor_mode=a.floor)
+            m.set_ranks(batches)
+            m.set_queries(records)
+            m.match_run(a.t, top_n=a.n, floor_mode=a.floor, merge_top_n=a.n if want_filter else 0)
+            res = m.fetch()
             for idx in loaded:
                 ix = m.indexes[idx]
                 text = format_cobs_text_fast(records, res, ix, strip_prefix=True)
                 out = os.path.join(a.match_dir, f"{ix.batch}____{qfile}.gz")
                 _atomic_write(out, text, gz=True)
-                merged_inputs.append(out)
                 print(f"[match-db] {ix.batch}: {len(res.units_of(idx))} queries with hits", file=sys.stderr)
+                refs_by_rank[ix.batch_rank] = [ix_ref for ix_ref in map(_ref_of, ix.doc_names)]
+            if want_filter:                                   # this round's top-N + ties per query
+                moffs, mc = m.merged()
+                q_of = np.repeat(np.arange(len(records), dtype=np.int64), np.diff(moffs.astype(np.int64)))
+                pieces.append((rec2qid[q_of], np.array(mc)))
             for idx in loaded:
                 m.evict(idx)
-        if a.filter_out:
-            fa = merge_match_files(m, a.q, sorted(merged_inputs), a.n, log=open(os.devnull, "w"))
+        if want_filter:
+            fa = _final_merge(m, queries, pieces, refs_by_rank, a.n)
             os.makedirs(os.path.dirname(os.path.abspath(a.filter_out)), exist_ok=True)
             _atomic_write(a.filter_out, fa.encode(), gz=False)
 
