@@ -267,6 +267,14 @@ def cmd_match_db(a):
             fa = _final_merge(m, queries, pieces, refs_by_rank, a.n)
             os.makedirs(os.path.dirname(os.path.abspath(a.filter_out)), exist_ok=True)
             _atomic_write(a.filter_out, fa.encode(), gz=False)
+            if a.bucket_dir:      # per-batch "reference -> queries to align" tables for stage 05
+                from .cobs_text import candidate_buckets, format_bucket_tsv
+                moffs, mc = m.merged()
+                buckets = candidate_buckets(list(queries), moffs, mc, refs_by_rank)
+                os.makedirs(a.bucket_dir, exist_ok=True)
+                for b in batches:
+                    _atomic_write(os.path.join(a.bucket_dir, f"{b}____{qfile}.candidates.tsv"),
+                                  format_bucket_tsv(buckets.get(brank[b], [])).encode(), gz=False)
 
 
 # ------------------------------------------------------------------------------------ argparse
@@ -340,6 +348,9 @@ def build_parser():
                    help="process only the batches the LPT plan gives to GPU I of N (one process per GPU); "
                         "run `filter` over all match files afterwards")
     d.add_argument("--load-workers", type=int, default=8, help="concurrent xz decoders while loading")
+    d.add_argument("--bucket-dir", default=None,
+                   help="also write {batch}____{qfile}.candidates.tsv (reference -> queries), the mapping "
+                        "batch_align.py:126-171 derives per batch from the 04_filter FASTA")
     d.add_argument("--round-bytes", type=int, default=0,
                    help="HBM bytes of indexes resident at once (default 90%% of --hbm-budget, else 160e9); "
                         "batches beyond it are streamed through in further rounds")

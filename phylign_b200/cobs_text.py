@@ -100,3 +100,31 @@ def format_filter_fasta_fast(records, merged_ptr, ref_names_by_rank) -> bytes:
         return C.string_at(out, n.value)
     finally:
         L.phy_text_free(out)
+
+
+# ---- 04 -> 05 hand-off -------------------------------------------------------
+def candidate_buckets(qnames, offs, cands, ref_names_by_rank):
+    """{batch_rank: [(ref, [qname, ...])]}: for every reference that is a candidate of at least one
+    query, the queries to align against it, in query-file order.  The same mapping
+    /root/reference/scripts/batch_align.py:126-171 (`load_qdicts`, rname_to_qnames) rebuilds for
+    every batch by re-parsing the whole 04_filter FASTA; emitted once here."""
+    n = len(cands)
+    if n == 0:
+        return {}
+    q_of = np.repeat(np.arange(len(qnames), dtype=np.int64), np.diff(np.asarray(offs).astype(np.int64)))
+    br = cands["batch_rank"].astype(np.int64)
+    dc = cands["doc"].astype(np.int64)
+    order = np.lexsort((q_of, dc, br))          # by batch, then reference, queries in file order
+    out = {}
+    i = 0
+    br_s, dc_s, q_s = br[order], dc[order], q_of[order]
+    cuts = np.flatnonzero((np.diff(br_s) != 0) | (np.diff(dc_s) != 0)) + 1
+    for lo, hi in zip(np.concatenate(([0], cuts)), np.concatenate((cuts, [n]))):
+        b, d = int(br_s[lo]), int(dc_s[lo])
+        out.setdefault(b, []).append((ref_names_by_rank[b][d], [qnames[q] for q in q_s[lo:hi].tolist()]))
+    return out
+
+
+def format_bucket_tsv(bucket) -> str:
+    """One line per reference: "<ref>\t<qname1>,<qname2>,..."."""
+    return "".join(f"{ref}\t{','.join(qs)}\n" for ref, qs in bucket)

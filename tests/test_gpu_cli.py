@@ -68,6 +68,23 @@ def test_match_db_writes_all_rule_outputs(tmp_path):
         assert got == H.golden_match_text(b, 3)
     assert out.read_text() == H.golden_filter_fa(3)
     assert not [f for f in os.listdir(mdir) if ".tmp." in f]
+    # 04 -> 05 hand-off tables: one per batch, every candidate of the FASTA appears exactly once
+    bdir = tmp_path / "buckets"
+    r = _run([sys.executable, "-m", "phylign_b200.cli", "match-db", "--cobs-dir", H.GOLDEN, "--batches",
+              str(batches), "-q", os.path.join(H.GOLDEN, "queries.fa"), "--match-dir", str(tmp_path / "m2"),
+              "--filter-out", str(tmp_path / "f2.fa"), "--bucket-dir", str(bdir), "-t", "0.7", "-n", "3"])
+    assert r.returncode == 0, r.stderr
+    pairs = set()
+    for b in H.GOLDEN_BATCHES:
+        for line in open(bdir / f"{b}____queries.candidates.tsv"):
+            ref, qs = line.rstrip("\n").split("\t")
+            pairs |= {(q, ref) for q in qs.split(",")}
+    want = set()
+    for line in H.golden_filter_fa(3).splitlines():
+        if line.startswith(">"):
+            name, _, com = line[1:].partition(" ")
+            want |= {(name, a) for a in com.split(",") if a}
+    assert pairs == want
     # a missing batch fails, and leaves no partial file behind
     batches.write_text("nosuch__01\n")
     r = _run([sys.executable, "-m", "phylign_b200.cli", "match-db", "--cobs-dir", H.GOLDEN, "--batches",

@@ -234,3 +234,40 @@ def test_fast_modulo_algorithm_is_exact():
         for n in ns + [rnd.randrange(1 << 64) for _ in range(200)] + [d - 1, d, d + 1, 2 * d - 1, 2 * d, M64 // d * d]:
             n &= M64
             assert fastmod(n, d) == n % d, (n, d)
+
+
+def test_candidate_buckets_equal_batch_align_load_qdicts():
+    """The per-batch reference -> queries tables equal what batch_align.py:126-171 (load_qdicts)
+    derives from the 04_filter FASTA (restated here on the golden file)."""
+    from phylign_b200.cobs_index import parse_bytes, ref_of
+    from phylign_b200.cobs_text import candidate_buckets, format_bucket_tsv
+    from phylign_b200.matcher import CAND_DT
+    keep = 3
+    refs = {}
+    for r, b in enumerate(sorted(H.GOLDEN_BATCHES)):
+        hdr, _ = parse_bytes(H.golden_index_bytes(b))
+        refs[r] = [ref_of(n) for n in hdr.doc_names]
+    acc_to = {a: (r, d) for r, names in refs.items() for d, a in enumerate(names)}
+    # parse the golden 04_filter FASTA the way readfq does: name, comment = candidate list
+    qnames, rows, offs = [], [], [0]
+    for line in H.golden_filter_fa(keep).splitlines():
+        if line.startswith(">"):
+            name, _, com = line[1:].partition(" ")
+            qnames.append(name)
+            for a in filter(len, com.split(",")):
+                r, d = acc_to[a]
+                rows.append((0, r, d, 0))
+            offs.append(len(rows))
+    cands = np.array(rows, dtype=CAND_DT)
+    got = candidate_buckets(qnames, np.array(offs, dtype=np.uint64), cands, refs)
+    # restatement of load_qdicts steps 2-3 per batch
+    for r, names in refs.items():
+        want = {}
+        for line in H.golden_filter_fa(keep).splitlines():
+            if line.startswith(">"):
+                name, _, com = line[1:].partition(" ")
+                for a in filter(len, com.split(",")):
+                    if a in names:
+                        want.setdefault(a, []).append(name)
+        assert dict(got.get(r, [])) == want
+        assert format_bucket_tsv(got.get(r, [])).count("\n") == len(want)
