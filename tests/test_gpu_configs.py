@@ -109,3 +109,63 @@ def test_config5_long_reads_threshold_sweep(M):
                     u = units[q]
                     assert int(u["n_pass"]) == n_pass, (thr, i, q)
                     assert [(int(h["doc"]), int(h["score"])) for h in res.hits_of(u)] == hits, (thr, i, q)
+
+
+def test_config4_all_305_batch_shapes_and_cross_batch_merge(M):
+    """Every document count of the 661k database (305 batches, rows of 13..500 B -> every
+    lanes-per-row class and stride) with small random signatures: per-batch hit lists and the
+    merged top-N + ties over 305 batches equal the oracle + the reference filter semantics."""
+    from oracle import filters
+    from phylign_b200.cobs_index import ClassicHeader, ref_of
+    _evict_all(M)
+    shapes = []
+    for line in open(os.path.join(H.GOLDEN, "db_shape.tsv")):
+        if not line.startswith("#"):
+            name, _, docs = line.split("\t")
+            shapes.append((name, int(docs)))
+    assert len(shapes) == 305
+    rng = np.random.default_rng(4)
+    sig = 1009
+    oidxs, ids = {}, {}
+    for name, docs in shapes:
+        names = [f"{int(x):07d}_S{docs}x{d}" for d, x in enumerate(np.sort(rng.integers(0, 10 ** 7, docs)))]
+        oi = oracle.OracleIndex.new(docs, sig, names)
+        body = oi.body
+        body[:] = rng.integers(0, 256, size=body.shape, dtype=np.uint8) & rng.integers(0, 256, size=body.shape, dtype=np.uint8)
+        if docs % 8:
+            body[:, -1] &= (1 << (docs % 8)) - 1
+        hdr = ClassicHeader(31, 1, docs, sig, 1, names)
+        ids[name] = M.load_index_bytes(hdr.to_bytes() + body.tobytes(), name)
+        oidxs[name] = oi
+    M.set_ranks([n for n, _ in shapes])
+    rnd = random.Random(4)
+    records = [(f"q{j}", "".join(rnd.choice("ACGT") for _ in range(rnd.choice([60, 150, 400])))) for j in range(24)]
+    M.set_queries(records)
+    thr, keep = 0.3, 5
+    M.match_run(thr, top_n=keep, merge_top_n=keep)
+    res = M.fetch()
+    offs, cands = M.merged()
+    per_batch = []
+    for name, docs in shapes:
+        units = {int(u["query"]): u for u in res.units_of(ids[name])}
+        oi = oidxs[name]
+        pq = []
+        for q, (qn, s) in enumerate(records):
+            k, hits = oi.query(s.encode(), thr)
+            n_pass = len(hits)
+            if n_pass > keep:
+                cut = hits[keep - 1][1]
+                hits = [h for h in hits if h[1] >= cut]
+            if n_pass:
+                u = units[q]
+                assert int(u["n_pass"]) == n_pass, (name, q)
+                assert [(int(h["doc"]), int(h["score"])) for h in res.hits_of(u)] == hits, (name, q)
+            else:
+                assert q not in units, (name, q)
+            pq.append((qn, [(ref_of(oi.doc_names[d]), sc) for d, sc in hits]))
+        per_batch.append((name, pq))
+    want = filters.merge_closed_form([(qn, s) for qn, s in records], per_batch, keep)
+    from phylign_b200.cobs_text import format_filter_fasta
+    refs = {ix.batch_rank: [ref_of(n) for n in ix.doc_names] for ix in M.indexes.values()}
+    assert format_filter_fasta(records, offs, cands, refs) == want
+    assert len(cands) >= 24 * keep
