@@ -520,6 +520,49 @@ __device__ __forceinline__ void csa_flush3(uint32_t (&pl)[P][4], uint32_t nb, co
     }
 }
 
+// Two-level variant for short queries (K <= 255, 8 planes): eights are paired into sixteens and
+// rippled every 2 batches, so the planes are exact counts after every even batch and the
+// pruning checkpoint can run every 16 rows instead of 32 (150-bp reads die at ~80 of 120 rows).
+template <int P>
+__device__ __forceinline__ void csa_batch2(uint32_t (&pl)[P][4], const uint4 (&v)[8], uint32_t j, uint32_t (&p8)[4]) {
+    static_assert(P >= 5, "two-level tree needs at least 5 planes");
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+        auto W = [&](const uint4& x) -> uint32_t { return w == 0 ? x.x : (w == 1 ? x.y : (w == 2 ? x.z : x.w)); };
+        uint32_t twoA, twoB, fourA, fourB, eight;
+        csa(twoA, pl[0][w], pl[0][w], W(v[0]), W(v[1]));
+        csa(twoB, pl[0][w], pl[0][w], W(v[2]), W(v[3]));
+        csa(fourA, pl[1][w], pl[1][w], twoA, twoB);
+        csa(twoA, pl[0][w], pl[0][w], W(v[4]), W(v[5]));
+        csa(twoB, pl[0][w], pl[0][w], W(v[6]), W(v[7]));
+        csa(fourB, pl[1][w], pl[1][w], twoA, twoB);
+        csa(eight, pl[2][w], pl[2][w], fourA, fourB);
+        if ((j & 1u) == 0) {
+            p8[w] = eight;
+        } else {
+            uint32_t carry;
+            csa(carry, pl[3][w], pl[3][w], p8[w], eight);
+#pragma unroll
+            for (int p = 4; p < P; p++) {
+                uint32_t t = pl[p][w] & carry;
+                pl[p][w] ^= carry;
+                carry = t;
+            }
+        }
+    }
+}
+template <int P>
+__device__ __forceinline__ void csa_flush2(uint32_t (&pl)[P][4], uint32_t nb, const uint32_t (&p8)[4]) {
+    if (nb & 1u) {
+#pragma unroll
+        for (int w = 0; w < 4; w++) {
+            uint32_t carry = p8[w];
+#pragma unroll
+            for (int p = 3; p < P; p++) { uint32_t t = pl[p][w] & carry; pl[p][w] ^= carry; carry = t; }
+        }
+    }
+}
+
 #ifndef PHY_RING_NB
 #define PHY_RING_NB 3
 #endif
@@ -543,6 +586,7 @@ __device__ __forceinline__ uint32_t ring_accumulate(uint32_t (&pl)[P][4], uint32
                                                 bool lane_on, uint32_t stride, uint64_t sig, uint64_t magic,
                                                 const uint64_t* __restrict__ hq, uint32_t nrows, uint32_t nmax,
                                                 int lane, uint32_t prune_T, unsigned gm) {
+    constexpr bool FINE = P <= 8;           // short queries: two-level tree, checkpoint every 2 batches
     constexpr int HB = LPR >= 8 ? LPR : 8;  // rows whose hashes are fetched per block
     constexpr int NH = HB / LPR;            // hashes per lane per block
     constexpr int BPH = HB / 8;             // batches per hash block
@@ -597,8 +641,9 @@ __device__ __forceinline__ uint32_t ring_accumulate(uint32_t (&pl)[P][4], uint32
             if (j * 8 + r < nrows && lane_on) v[r] = lds128(src + r * 512);
             else v[r] = make_uint4(0, 0, 0, 0);
         }
-        csa_batch3<P>(pl, v, j, p8, p16);
-        if (prune_any && ((j + 1) & 3u) == 0) {  // planes are exact counts here
+        if constexpr (FINE) csa_batch2<P>(pl, v, j, p8);
+        else csa_batch3<P>(pl, v, j, p8, p16);
+        if (prune_any && ((j + 1) & (FINE ? 1u : 3u)) == 0) {  // planes are exact counts here
             const uint32_t x = min((j + 1) * 8u, nrows);  // rows of this unit counted so far
             bool alive = lane_on;
             if (lane_on && prune_T != 0 && prune_T + x > K) {  // need = T - (K - x) more than zero
@@ -621,7 +666,8 @@ __device__ __forceinline__ uint32_t ring_accumulate(uint32_t (&pl)[P][4], uint32
         issue(j + NB);  // refill the slot: its values were consumed above by this very lane
     }
     cp_async_wait<0>();
-    csa_flush3<P>(pl, j, p8, p16);
+    if constexpr (FINE) csa_flush2<P>(pl, j, p8);
+    else csa_flush3<P>(pl, j, p8, p16);
     return min(j * 8u, K);  // rows of this unit that were fetched and counted
 }
 
@@ -1037,19 +1083,21 @@ int phy_launch_scores(phy_ctx* ctx, int idx_id, uint32_t* d_out_scores) {
 }
 
 int phy_launch_gather(phy_ctx* ctx, const phy_match_params* p) {
-    // per-query minimum score T (host double arithmetic, identical to the oracle / cobs)
-    // fastq = fused in one kernel: K <= 1023 (10 counter planes) first, then K <= 16383 (14 planes,
-    // ring kernel only); slowq = longer queries, chunked through the dense-score path
-    std::vector<uint32_t> T(ctx->nq), fastq, midq, slowq;
-    const bool have_p14 = ctx->kernel_path == 3;
+    // per-query minimum score T (host double arithmetic, identical to the oracle / cobs) and the
+    // query classes by k-mer count: <= 255 (8 counter planes), <= 1023 (10), <= 16383 (14) are fused
+    // in the ring kernel; longer ones go through the chunked dense-score path.  Indexes the ring
+    // kernel cannot take (several hash functions, or a forced legacy kernel path) fuse K <= 1023
+    // with 10 planes and send everything longer through the general path.
+    std::vector<uint32_t> T(ctx->nq), shortq, fastq, midq, slowq;
     for (uint32_t q = 0; q < ctx->nq; q++) {
         double x = p->threshold * (double)ctx->h_nk[q];
         double r = p->floor_mode ? floor(x) : ceil(x);
         T[q] = r < 0 ? 0u : (r > 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)r);
         const uint32_t K = ctx->h_nk[q];
         if (K == 0) continue;
-        if (K <= PHY_FUSED_KMAX) fastq.push_back(q);
-        else if (have_p14 && K <= PHY_LONG_KMAX) midq.push_back(q);
+        if (K <= PHY_SHORT_KMAX) shortq.push_back(q);
+        else if (K <= PHY_FUSED_KMAX) fastq.push_back(q);
+        else if (K <= PHY_LONG_KMAX) midq.push_back(q);
         else slowq.push_back(q);
     }
     // longest first: balances the tail and keeps co-resident groups of a warp similar
@@ -1064,10 +1112,16 @@ int phy_launch_gather(phy_ctx* ctx, const phy_match_params* p) {
         for (uint32_t q : v) out[start[kmax - ctx->h_nk[q]]++] = q;
         v.swap(out);
     };
+    sort_by_len_desc(shortq);
     sort_by_len_desc(fastq);
     sort_by_len_desc(midq);
-    const uint32_t n_fast10 = (uint32_t)fastq.size(), n_fast14 = (uint32_t)midq.size();
-    fastq.insert(fastq.end(), midq.begin(), midq.end());   // [P10 queries | P14 queries]
+    // device list layout: [10-plane | 8-plane | 14-plane]; the first two together are "K <= 1023"
+    const uint32_t n_fast8 = (uint32_t)shortq.size(), n_fast10 = (uint32_t)fastq.size(), n_fast14 = (uint32_t)midq.size();
+    const uint32_t n_le1023 = n_fast10 + n_fast8;
+    std::vector<uint32_t> le1023 = fastq;
+    le1023.insert(le1023.end(), shortq.begin(), shortq.end());
+    fastq = le1023;
+    fastq.insert(fastq.end(), midq.begin(), midq.end());   // every fused-capable query
     PHY_TRY(phy_ensure(ctx, ctx->d_T, ctx->nq + 1));
     PHY_TRY(phy_h2d(ctx, ctx->d_T.p, T.data(), T.size() * sizeof(uint32_t)));
     PHY_TRY(phy_ensure(ctx, ctx->d_qlist, ctx->nq + 1));
@@ -1076,18 +1130,21 @@ int phy_launch_gather(phy_ctx* ctx, const phy_match_params* p) {
     PHY_TRY(phy_ensure(ctx, ctx->d_counters, 8));
 
     // index classes
-    std::vector<uint32_t> cls[6], wide;  // lpr 1,2,4,8,16,32 ; wide = stride > 512 (general path)
+    // cls[0..5]: ring-kernel indexes by lanes-per-row 1,2,4,8,16,32; cls[6..11]: the same for
+    // indexes on a legacy kernel; rows wider than 512 B take the general path for every query
+    auto ring_ok = [&](const HostIndex& ix) { return ix.d.num_hashes == 1 && ctx->kernel_path == 3; };
+    std::vector<uint32_t> cls[12];
     for (size_t i = 0; i < ctx->idx.size(); i++) {
         const HostIndex& ix = ctx->idx[i];
         if (!ix.alive || !ix.committed || !ix.active) continue;
-        if (ix.d.stride > PHY_CHUNK_BYTES) { wide.push_back((uint32_t)i); continue; }
+        if (ix.d.stride > PHY_CHUNK_BYTES) continue;
         int c = 0;
         while ((1 << c) < ix.lpr) c++;
-        cls[c].push_back((uint32_t)i);
+        cls[ring_ok(ix) ? c : c + 6].push_back((uint32_t)i);
     }
     std::vector<uint32_t> class_flat;
-    size_t class_off[6];
-    for (int c = 0; c < 6; c++) { class_off[c] = class_flat.size(); class_flat.insert(class_flat.end(), cls[c].begin(), cls[c].end()); }
+    size_t class_off[12];
+    for (int c = 0; c < 12; c++) { class_off[c] = class_flat.size(); class_flat.insert(class_flat.end(), cls[c].begin(), cls[c].end()); }
     uint32_t* d_class = nullptr;
     if (!class_flat.empty()) {
         PHY_TRY(phy_ensure(ctx, ctx->d_class, class_flat.size()));
@@ -1130,35 +1187,37 @@ int phy_launch_gather(phy_ctx* ctx, const phy_match_params* p) {
             a.unit_id = ctx->d_unit_id.p;
         }
         if (!fastq.empty()) {
-            for (int c = 0; c < 6; c++) {
+            for (int c = 0; c < 6; c++) {  // path C: lane-private cp.async ring, persistent warps
                 if (cls[c].empty()) continue;
                 a.class_idx = d_class + class_off[c];
                 a.n_class_idx = (uint32_t)cls[c].size();
-                bool multi_hash = false;
-                for (uint32_t i : cls[c]) multi_hash |= ctx->idx[i].d.num_hashes > 1;
-                const bool ring = !multi_hash && ctx->kernel_path == 3;
-                if (ring) {  // path C: lane-private cp.async ring, persistent warps
-                    for (int pass = 0; pass < 2; pass++) {   // 10-plane queries, then 14-plane queries
-                        a.qlist = ctx->d_qlist.p + (pass ? n_fast10 : 0);
-                        a.n_q = pass ? n_fast14 : n_fast10;
-                        if (a.n_q == 0) continue;
-                        PHY_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p + 3, 0, sizeof(unsigned long long), ctx->stream));
-                        int rc = pass ? dispatch_ring<14>(c, a, ctx->stream, ctx->n_sm)
-                                      : dispatch_ring<10>(c, a, ctx->stream, ctx->n_sm);
-                        if (rc != 0) {
-                            phy_set_error(ctx, "cannot configure the ring gather kernel: %s",
-                                          cudaGetErrorString(cudaGetLastError()));
-                            return PHY_ERR_CUDA;
-                        }
-                        ctx->launches++;
-                        PHY_CUDA(ctx, cudaGetLastError());
+                for (int pass = 0; pass < 3; pass++) {   // 10-plane, 8-plane, 14-plane query classes
+                    a.qlist = ctx->d_qlist.p + (pass == 0 ? 0 : pass == 1 ? n_fast10 : n_le1023);
+                    a.n_q = pass == 0 ? n_fast10 : pass == 1 ? n_fast8 : n_fast14;
+                    if (a.n_q == 0) continue;
+                    PHY_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p + 3, 0, sizeof(unsigned long long), ctx->stream));
+                    int rc = pass == 0 ? dispatch_ring<10>(c, a, ctx->stream, ctx->n_sm)
+                           : pass == 1 ? dispatch_ring<8>(c, a, ctx->stream, ctx->n_sm)
+                                       : dispatch_ring<14>(c, a, ctx->stream, ctx->n_sm);
+                    if (rc != 0) {
+                        phy_set_error(ctx, "cannot configure the ring gather kernel: %s",
+                                      cudaGetErrorString(cudaGetLastError()));
+                        return PHY_ERR_CUDA;
                     }
-                    a.qlist = ctx->d_qlist.p; a.n_q = n_fast10;
-                    continue;
+                    ctx->launches++;
+                    PHY_CUDA(ctx, cudaGetLastError());
                 }
-                // paths A/B know 10 planes only: the 14-plane queries were routed to slowq above
+            }
+            a.qlist = ctx->d_qlist.p;
+            a.n_q = n_le1023;              // legacy kernels hold 10 planes: every query with K <= 1023
+            for (int c = 0; c < 6 && a.n_q; c++) {
+                if (cls[c + 6].empty()) continue;
+                a.class_idx = d_class + class_off[c + 6];
+                a.n_class_idx = (uint32_t)cls[c + 6].size();
+                bool multi_hash = false;
+                for (uint32_t i : cls[c + 6]) multi_hash |= ctx->idx[i].d.num_hashes > 1;
                 const bool bulk = c >= 3 && !multi_hash && ctx->kernel_path == 2;
-                if (bulk) {  // persistent warps pull units from counters[3]
+                if (bulk) {  // path B: cp.async.bulk ring
                     PHY_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p + 3, 0, sizeof(unsigned long long), ctx->stream));
                     int rc = c == 3 ? launch_bulk<8, BULK_NB, BULK_WARPS>(a, ctx->stream, ctx->n_sm)
                            : c == 4 ? launch_bulk<16, BULK_NB, BULK_WARPS>(a, ctx->stream, ctx->n_sm)
@@ -1168,7 +1227,7 @@ int phy_launch_gather(phy_ctx* ctx, const phy_match_params* p) {
                                       cudaGetErrorString(cudaGetLastError()));
                         return PHY_ERR_CUDA;
                     }
-                } else switch (c) {
+                } else switch (c) {  // path A: rows straight to registers (also: several hash functions)
                     case 0: launch_fused<1>(a, ctx->stream); break;
                     case 1: launch_fused<2>(a, ctx->stream); break;
                     case 2: launch_fused<4>(a, ctx->stream); break;
@@ -1187,6 +1246,7 @@ int phy_launch_gather(phy_ctx* ctx, const phy_match_params* p) {
             const bool is_wide = ix.d.stride > PHY_CHUNK_BYTES;
             std::vector<uint32_t> qs = slowq;
             if (is_wide) qs.insert(qs.end(), fastq.begin(), fastq.end());
+            else if (!ring_ok(ix)) qs.insert(qs.end(), midq.begin(), midq.end());  // K > 1023 on a legacy kernel
             if (qs.empty()) continue;
             // bounded scratch: process slots in groups of <= 256 MB of scores
             size_t per = std::max<size_t>(1, (size_t)(64u << 20) / std::max<uint32_t>(1, ix.d.n_docs));

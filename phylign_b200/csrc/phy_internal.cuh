@@ -14,6 +14,7 @@
 #define PHY_ROW_INVALID 0xFFFFFFFFu
 #define PHY_FUSED_PLANES 10           // vertical counter planes of the fused kernel
 #define PHY_FUSED_KMAX ((1u << PHY_FUSED_PLANES) - 1u)
+#define PHY_SHORT_KMAX ((1u << 8) - 1u)   // 8 planes: reads up to 285 bp, pruning checkpoint every 16 rows
 #define PHY_LONG_KMAX ((1u << 14) - 1u)   // 14 planes: fused up to 16383 k-mers (10 kbp reads)
 #define PHY_CHUNK_BYTES 512u          // one warp-wide 128-bit load = 512 B of a row
 

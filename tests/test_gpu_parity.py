@@ -355,3 +355,33 @@ def test_c_abi_state_and_argument_errors(M):
     assert L.phy_ctx_set_option(ctx, b"nonsense", 1) == -2
     assert L.phy_index_evict(ctx, i) == 0 and L.phy_index_evict(ctx, i) == -2
     assert L.phy_ctx_create(C.byref(C.c_void_p()), 4096, 0) == -2                         # no such device
+
+
+@pytest.mark.parametrize("nh,path", [(2, "3"), (1, "1"), (1, "2"), (1, "3")])
+def test_every_query_length_class_on_every_kernel_path(nh, path):
+    """K = 40 .. 20000 (8-, 10-, 14-plane and chunked classes) against an index the ring kernel
+    cannot take (2 hash functions) and on each forced kernel path: no query may be dropped."""
+    import subprocess, sys
+    code = r'''
+import os, sys, random
+sys.path.insert(0, %r)
+import oracle
+from phylign_b200.matcher import Matcher
+from tests.test_gpu_parity import _check_against_oracle
+nh = %d
+spec = oracle.SynthSpec(seed=91, n_docs=700, genome_len=21000, clade_size=8, clade_sub_q16=655, doc_sub_q16=655)
+docs = [oracle.synth_genome(spec, d) if d %% 50 == 0 else b"" for d in range(spec.n_docs)]
+oidx = oracle.OracleIndex.construct(docs, num_hashes=nh, signature_size_override=30011)
+oidx.write("/tmp/phy_cls.cobs_classic")
+m = Matcher(0)
+i = m.load_index("/tmp/phy_cls.cobs_classic", batch="cls__01")
+g = docs[0].decode()
+records = [(f"L{ln}", g[7:7 + ln]) for ln in (40, 70, 285, 286, 600, 1053, 1054, 5000, 16413, 16414, 20000)]
+m.set_queries(records)
+_check_against_oracle(m, i, oidx, records, 0.7, 3)
+_check_against_oracle(m, i, oidx, records, 0.2, 0)
+print("ok")
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), nh)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True,
+                       env=dict(os.environ, PHY_KERNEL_PATH=path))
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), (r.stdout + r.stderr)[-3000:]
