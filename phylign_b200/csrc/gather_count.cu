@@ -569,6 +569,9 @@ __device__ __forceinline__ void csa_flush2(uint32_t (&pl)[P][4], uint32_t nb, co
 #ifndef PHY_RING_WARPS
 #define PHY_RING_WARPS 4
 #endif
+#ifndef PHY_RING_NB_SHORT
+#define PHY_RING_NB_SHORT 2
+#endif
 constexpr int RING_NB = PHY_RING_NB, RING_WARPS = PHY_RING_WARPS;
 
 // One unit per group of LPR lanes: add the rows of its `nrows` k-mers (hashes at hq) into pl.
@@ -957,13 +960,16 @@ int launch_ring(const GatherArgs& a, cudaStream_t st, int n_sm) {
 }
 template <int P>
 int dispatch_ring(int c, const GatherArgs& a, cudaStream_t st, int n_sm) {
+    // short-read class (8 planes, ~92 registers): a 2-deep ring (8 KB per warp) lets 20 warps per SM
+    // be resident instead of 16, which covers the start-up bubble of its short units
+    constexpr int NB = P <= 8 ? PHY_RING_NB_SHORT : RING_NB;
     switch (c) {
-        case 0: return launch_ring<1, P, RING_NB, RING_WARPS>(a, st, n_sm);
-        case 1: return launch_ring<2, P, RING_NB, RING_WARPS>(a, st, n_sm);
-        case 2: return launch_ring<4, P, RING_NB, RING_WARPS>(a, st, n_sm);
-        case 3: return launch_ring<8, P, RING_NB, RING_WARPS>(a, st, n_sm);
-        case 4: return launch_ring<16, P, RING_NB, RING_WARPS>(a, st, n_sm);
-        default: return launch_ring<32, P, RING_NB, RING_WARPS>(a, st, n_sm);
+        case 0: return launch_ring<1, P, NB, RING_WARPS>(a, st, n_sm);
+        case 1: return launch_ring<2, P, NB, RING_WARPS>(a, st, n_sm);
+        case 2: return launch_ring<4, P, NB, RING_WARPS>(a, st, n_sm);
+        case 3: return launch_ring<8, P, NB, RING_WARPS>(a, st, n_sm);
+        case 4: return launch_ring<16, P, NB, RING_WARPS>(a, st, n_sm);
+        default: return launch_ring<32, P, NB, RING_WARPS>(a, st, n_sm);
     }
 }
 
