@@ -104,10 +104,13 @@ extern "C" int phy_ctx_create(phy_ctx** out, int device, uint64_t hbm_budget) {
     return PHY_OK;
 }
 
+void phy_nccl_shutdown(phy_ctx* ctx);
+
 extern "C" void phy_ctx_destroy(phy_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    phy_nccl_shutdown(ctx);
     for (auto& ix : ctx->idx) {
         if (ix.rows_mut) cudaFree(ix.rows_mut);
         if (ix.ref_rank_mut) cudaFree(ix.ref_rank_mut);

@@ -134,6 +134,13 @@ extern "C" int phy_nccl_init(phy_ctx* ctx, const void* id, int rank, int n_ranks
     return PHY_OK;
 }
 
+void phy_nccl_shutdown(phy_ctx* ctx) {
+    if (ctx->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)ctx->nccl_comm);
+    ctx->nccl_comm = nullptr;
+    ctx->n_ranks = 1;
+    ctx->rank = 0;
+}
+
 // After the local merge: gather every rank's (d_foffs, d_final) on rank 0 and merge again.
 int phy_nccl_merge(phy_ctx* ctx, uint32_t top_n) {
     ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
