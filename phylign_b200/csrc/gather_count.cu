@@ -674,8 +674,11 @@ __device__ __forceinline__ uint32_t ring_accumulate(uint32_t (&pl)[P][4], uint32
     return min(j * 8u, K);  // rows of this unit that were fetched and counted
 }
 
+#ifndef PHY_RING_MINBLOCKS
+#define PHY_RING_MINBLOCKS 1
+#endif
 template <int LPR, int P, int NB, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) gather_count_ring_kernel(const GatherArgs a) {
+__global__ void __launch_bounds__(WARPS * 32, PHY_RING_MINBLOCKS) gather_count_ring_kernel(const GatherArgs a) {
     constexpr int G = 32 / LPR;
     extern __shared__ __align__(128) uint8_t smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;

@@ -1,0 +1,53 @@
+"""bench.py contract checks that need no GPU: workload arithmetic, placement, reference-arm JSON."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+
+def ns(**kw):
+    d = dict(workload="reads1k", db_scale=1.0, indexes=64, docs=4000, genome_len=1_000_000, reads=100_000,
+             read_len=1000)
+    d.update(kw)
+    return argparse.Namespace(**d)
+
+
+def test_config3_workload_numbers_match_baseline_md():
+    w = bench.workload(ns())
+    assert w["alg_bytes"] == 3_104_000_000_000          # 3.104 TB
+    assert w["kmer_docs"] == 100_000 * 970 * 64 * 4000
+    assert abs(w["signature_size"] / 999_970 - 2.8037) < 1e-3
+    assert w["bases"] == 10 ** 8
+
+
+def test_config4_workload_is_the_661k_database_shape():
+    w = bench.workload(ns(workload="db661k"))
+    assert w["n_indexes"] == 305 and w["row_bytes_per_kmer"] == 82741
+    assert abs(w["alg_bytes"] / 1e12 - 8.03) < 0.01       # 8.03 TB per 1e8 bases
+    total = sum(b["signature_size"] * ((b["n_docs"] + 7) // 8) for b in w["batches"])
+    assert abs(total / 1.058455434059e12 - 1) < 1e-3      # decompressed database size
+    placement, imbalance = bench.place(w, 8, 170 * 10 ** 9)
+    assert sum(len(p) for p in placement) == 305 and imbalance < 1.02
+    small = bench.workload(ns(workload="db661k", db_scale=0.05))
+    assert len(bench.place(small, 1, 170 * 10 ** 9)[0][0]) == 305
+
+
+def test_reference_arm_prints_the_contract_line():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--reads", "120",
+                        "--read-len", "150", "--indexes", "2", "--docs", "64", "--genome-len", "2000",
+                        "--steps", "2", "--warmup", "1"], capture_output=True, text=True,
+                       env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+              "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "bases/s" and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"] > 0
+    assert "workload" in d["config"] and "model" not in d["config"]
