@@ -7,15 +7,24 @@
 //
 // Shape of the work: for every (query, index) and every query k-mer, one row of the
 // bit-sliced index (ceil(D/8) bytes, random address) is read from HBM and added into D
-// per-document counters.  HBM-bound: one 128-bit load per lane per row chunk, and the
-// counters are VERTICAL (bit-sliced): plane p of a lane holds bit p of the counters of
-// the 128 documents that lane owns, so adding a row costs ~3.5 LOP3 per 32 documents
-// (Harley-Seal carry-save over blocks of 8 rows, then a ripple into the upper planes)
-// instead of one add per document.  Threshold and top-N cut are evaluated bit-sliced on
-// the planes; only passing documents ever get their score extracted.
+// per-document counters.  HBM-bound: one 16-B piece per lane per row, and the counters are
+// VERTICAL (bit-sliced): plane p of a lane holds bit p of the counters of the 128 documents
+// that lane owns, so adding a row costs 2-3 LOP3 per 32 documents (Harley-Seal carry-save
+// tree over blocks of 8/16/32 rows, then a ripple into the upper planes) instead of one add
+// per document.  Threshold, top-N cut and the exact threshold pruning are evaluated
+// bit-sliced on the planes; only kept documents ever get their score extracted.
 //
-// Geometry: a row is covered by LPR lanes x 16 B (LPR = 1..32, a power of two chosen
-// from the row stride); a warp holds 32/LPR independent (query,index) units.
+// Geometry: a row is covered by LPR lanes x 16 B (LPR = 1..32, a power of two chosen from the
+// row stride); a warp holds 32/LPR independent (query,index) units.
+//
+// Three generations of the fused kernel live here (profiles/):
+//   path A  gather_count_fused_kernel   rows -> registers, 8 loads in flight per lane (latency
+//                                       bound, 0.68 of the copy peak; still used for h > 1)
+//   path B  gather_count_bulk_kernel    per-warp smem ring fed by cp.async.bulk + mbarriers
+//   path C  gather_count_ring_kernel    per-warp smem ring fed by lane-private cp.async.cg,
+//                                       persistent warps, 8/10/14 counter planes, exact
+//                                       threshold pruning -- the default (90 % of DRAM peak)
+//   general accum_scores_ring_kernel + select_scores_kernel: K > 16383, D > 4096, phy_scores
 #include "phy_internal.cuh"
 
 #include <algorithm>
