@@ -25,6 +25,7 @@ import argparse
 import gzip
 import os
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
@@ -250,13 +251,19 @@ def cmd_match_db(a):
             m.set_queries(records)
             m.match_run(a.t, top_n=a.n, floor_mode=a.floor, merge_top_n=a.n if want_filter else 0)
             res = m.fetch()
-            for idx in loaded:
+
+            def write_one(idx):       # format (C++) + gzip (zlib) both release the GIL: one thread per file
                 ix = m.indexes[idx]
                 text = format_cobs_text_fast(records, res, ix, strip_prefix=True)
-                out = os.path.join(a.match_dir, f"{ix.batch}____{qfile}.gz")
-                _atomic_write(out, text, gz=True)
-                print(f"[match-db] {ix.batch}: {len(res.units_of(idx))} queries with hits", file=sys.stderr)
-                refs_by_rank[ix.batch_rank] = [ix_ref for ix_ref in map(_ref_of, ix.doc_names)]
+                _atomic_write(os.path.join(a.match_dir, f"{ix.batch}____{qfile}.gz"), text, gz=True)
+                return idx
+
+            format_cobs_text_fast(records, res, m.indexes[loaded[0]], strip_prefix=True)   # warm the header cache
+            with ThreadPoolExecutor(max_workers=max(1, a.load_workers)) as ex:
+                for idx in ex.map(write_one, loaded):
+                    ix = m.indexes[idx]
+                    print(f"[match-db] {ix.batch}: {len(res.units_of(idx))} queries with hits", file=sys.stderr)
+                    refs_by_rank[ix.batch_rank] = [_ref_of(n) for n in ix.doc_names]
             if want_filter:                                   # this round's top-N + ties per query
                 moffs, mc = m.merged()
                 q_of = np.repeat(np.arange(len(records), dtype=np.int64), np.diff(moffs.astype(np.int64)))

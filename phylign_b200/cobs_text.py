@@ -58,6 +58,9 @@ def _cat(strings):
     return b"".join(bs), offs
 
 
+_HDR_CACHE = (None, None, None)
+
+
 def format_cobs_text_fast(records, result, index, strip_prefix: bool = False, results_ptr=None) -> bytes:
     """Same bytes as format_cobs_text(...).encode(), via phy_format_cobs_text.
     `results_ptr`: ctypes POINTER(Results) (defaults to the one backing `result`)."""
@@ -65,8 +68,11 @@ def format_cobs_text_fast(records, result, index, strip_prefix: bool = False, re
     from . import _lib
     L = _lib.load()
     rp = results_ptr if results_ptr is not None else result._owner.ptr
-    hcat, hoffs = _cat([h for h, _ in records])
-    skip = np.array([len(s) == 0 for _, s in records], dtype=np.uint8)
+    global _HDR_CACHE          # the same record list is formatted once per index: build its arrays once
+    if _HDR_CACHE[0] is not records:
+        _HDR_CACHE = (records, _cat([h for h, _ in records]),
+                      np.array([len(s) == 0 for _, s in records], dtype=np.uint8))
+    (hcat, hoffs), skip = _HDR_CACHE[1], _HDR_CACHE[2]
     if not hasattr(index, "_names_cat"):
         index._names_cat = _cat(index.doc_names)
     ncat, noffs = index._names_cat
