@@ -14,7 +14,13 @@
     python -m phylign_b200.cli match-db --cobs-dir DIR --batches FILE -q QUERY.fa
                                         --match-dir intermediate/03_match --filter-out OUT.fa
         all batches in one resident context: writes every {batch}____{qfile}.gz and the
-        04_filter FASTA (replaces 305 `decompress_and_run_cobs` jobs + `translate_matches`)
+        04_filter FASTA (replaces 305 `decompress_and_run_cobs` jobs + `translate_matches`);
+        --shard I/N (one process per GPU), --round-bytes (stream batches that do not fit),
+        --resume, --bucket-dir (reference -> queries tables for stage 05)
+    python -m phylign_b200.cli serve --socket SOCK [--preload INDEX ...]
+        resident server: indexes stay in HBM, `cobs query --server SOCK` / $PHYLIGN_SERVER
+    python -m phylign_b200.cli fix-query INPUT.f[aq] ...
+        seqtk seq -A -U -C | awk non-ACGT->A of Snakefile:326-332, inputs concatenated
 
 Any failure exits non-zero and leaves nothing partial at the output paths (the rules run
 under `set -euo pipefail`, Snakefile:142).
