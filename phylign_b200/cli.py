@@ -64,6 +64,19 @@ def _postprocess_stream(fin, fout, keep: int):
             fout.write(y)
 
 
+def query_blocks(records, max_bases: int):
+    """Split the query list into consecutive blocks of at most max_bases bases (at least one
+    record each): the k-mer hashes of a block (8 B per base) must fit in HBM beside the indexes."""
+    start, acc = 0, 0
+    for i, (_, seq) in enumerate(records):
+        if i > start and acc + len(seq) > max_bases:
+            yield start, records[start:i]
+            start, acc = i, 0
+        acc += len(seq)
+    if start < len(records) or not records:
+        yield start, records[start:]
+
+
 # ------------------------------------------------------------------------------------ cobs query
 def cmd_cobs_query(a):
     server = getattr(a, "server", None) or os.environ.get("PHYLIGN_SERVER")
@@ -84,9 +97,10 @@ def cmd_cobs_query(a):
         hdr = m.indexes[idx].header
         if a.index_sizes is not None and a.index_sizes != hdr.header_size + hdr.body_size:
             _die(f"--index-sizes {a.index_sizes} != header {hdr.header_size} + body {hdr.body_size}")
-        m.set_queries(records)
-        res = m.match(a.t, top_n=a.top_n, floor_mode=a.floor)
-        sys.stdout.buffer.write(format_cobs_text_fast(records, res, m.indexes[idx], strip_prefix=a.top_n > 0))
+        for _, block in query_blocks(records, a.query_block_bases):
+            m.set_queries(block)
+            res = m.match(a.t, top_n=a.top_n, floor_mode=a.floor)
+            sys.stdout.buffer.write(format_cobs_text_fast(block, res, m.indexes[idx], strip_prefix=a.top_n > 0))
     sys.stdout.buffer.flush()
 
 
@@ -254,26 +268,33 @@ def cmd_match_db(a):
                 continue
             loaded = m.load_indexes([path_of(b) for b in mine], mine, workers=a.load_workers)
             m.set_ranks(batches)
-            m.set_queries(records)
-            m.match_run(a.t, top_n=a.n, floor_mode=a.floor, merge_top_n=a.n if want_filter else 0)
-            res = m.fetch()
+            texts = {idx: [] for idx in loaded}               # per index: one text piece per query block
+            n_hit_queries = {idx: 0 for idx in loaded}
+            for q0, block in query_blocks(records, a.query_block_bases):
+                m.set_queries(block)
+                m.match_run(a.t, top_n=a.n, floor_mode=a.floor, merge_top_n=a.n if want_filter else 0)
+                res = m.fetch()
+                format_cobs_text_fast(block, res, m.indexes[loaded[0]], strip_prefix=True)   # warm the header cache
+                with ThreadPoolExecutor(max_workers=max(1, a.load_workers)) as ex:   # C++ formatter releases the GIL
+                    for idx, text in zip(loaded, ex.map(
+                            lambda i: format_cobs_text_fast(block, res, m.indexes[i], strip_prefix=True), loaded)):
+                        texts[idx].append(text)
+                        n_hit_queries[idx] += len(res.units_of(idx))
+                if want_filter:                               # this block's top-N + ties per query and round
+                    moffs, mc = m.merged()
+                    q_of = q0 + np.repeat(np.arange(len(block), dtype=np.int64), np.diff(moffs.astype(np.int64)))
+                    pieces.append((rec2qid[q_of], np.array(mc)))
 
-            def write_one(idx):       # format (C++) + gzip (zlib) both release the GIL: one thread per file
+            def write_one(idx):       # gzip (zlib) releases the GIL: one thread per file
                 ix = m.indexes[idx]
-                text = format_cobs_text_fast(records, res, ix, strip_prefix=True)
-                _atomic_write(os.path.join(a.match_dir, f"{ix.batch}____{qfile}.gz"), text, gz=True)
+                _atomic_write(os.path.join(a.match_dir, f"{ix.batch}____{qfile}.gz"), b"".join(texts[idx]), gz=True)
                 return idx
 
-            format_cobs_text_fast(records, res, m.indexes[loaded[0]], strip_prefix=True)   # warm the header cache
             with ThreadPoolExecutor(max_workers=max(1, a.load_workers)) as ex:
                 for idx in ex.map(write_one, loaded):
                     ix = m.indexes[idx]
-                    print(f"[match-db] {ix.batch}: {len(res.units_of(idx))} queries with hits", file=sys.stderr)
+                    print(f"[match-db] {ix.batch}: {n_hit_queries[idx]} queries with hits", file=sys.stderr)
                     refs_by_rank[ix.batch_rank] = [_ref_of(n) for n in ix.doc_names]
-            if want_filter:                                   # this round's top-N + ties per query
-                moffs, mc = m.merged()
-                q_of = np.repeat(np.arange(len(records), dtype=np.int64), np.diff(moffs.astype(np.int64)))
-                pieces.append((rec2qid[q_of], np.array(mc)))
             for idx in loaded:
                 m.evict(idx)
         if want_filter:
@@ -307,6 +328,8 @@ def build_parser():
     q.add_argument("--top-n", type=int, default=0, help="fuse postprocess_cobs.py -n N (names get the '_acc' form)")
     q.add_argument("--floor", action="store_true", help="threshold = floor(t*K) instead of ceil (SURVEY A.6)")
     q.add_argument("--device", type=int, default=0)
+    q.add_argument("--query-block-bases", type=int, default=2 * 10 ** 9,
+                   help="process the queries in blocks of at most this many bases (HBM for the hashes)")
     q.add_argument("--server", default=None, help="socket of a resident `serve` process (or $PHYLIGN_SERVER)")
     q.set_defaults(fn=cmd_cobs_query)
 
@@ -319,7 +342,7 @@ def build_parser():
     r.add_argument("--device", type=int, default=0)
     r.set_defaults(fn=lambda a: cmd_cobs_query(argparse.Namespace(
         t=a.kmer_thres, T=0, i=a.cobs_index_xz, index_sizes=a.uncompressed_size, f=a.query, top_n=0,
-        floor=False, device=a.device)))
+        floor=False, device=a.device, query_block_bases=2 * 10 ** 9)))
 
     sv = sub.add_parser("serve", help="keep indexes resident in HBM and answer `cobs query --server` requests")
     sv.add_argument("--socket", required=True)
@@ -361,6 +384,8 @@ def build_parser():
                    help="process only the batches the LPT plan gives to GPU I of N (one process per GPU); "
                         "run `filter` over all match files afterwards")
     d.add_argument("--load-workers", type=int, default=8, help="concurrent xz decoders while loading")
+    d.add_argument("--query-block-bases", type=int, default=2 * 10 ** 9,
+                   help="process the queries in blocks of at most this many bases (HBM for the hashes)")
     d.add_argument("--bucket-dir", default=None,
                    help="also write {batch}____{qfile}.candidates.tsv (reference -> queries), the mapping "
                         "batch_align.py:126-171 derives per batch from the 04_filter FASTA")

@@ -172,3 +172,22 @@ def test_resident_server_answers_cobs_queries(tmp_path):
             srv.wait(timeout=30)
         except Exception:
             srv.kill()
+
+
+def test_query_blocks_do_not_change_the_output(tmp_path):
+    """Queries processed in several HBM-sized blocks: same bytes as in one block."""
+    xz = os.path.join(H.GOLDEN, "aaa__01.cobs_classic.xz")
+    r = _run([f"{ROOT}/scripts/cobs", "query", "-t", "0.7", "-i", xz, "-f", f"{H.GOLDEN}/queries.fa",
+              "--query-block-bases", "700"])
+    assert r.returncode == 0 and r.stdout == H.golden_cobs_text("aaa__01"), r.stderr
+    batches = tmp_path / "batches.txt"
+    batches.write_text("\n".join(H.GOLDEN_BATCHES) + "\n")
+    mdir, out = tmp_path / "03_match", tmp_path / "q.fa"
+    r = _run([sys.executable, "-m", "phylign_b200.cli", "match-db", "--cobs-dir", H.GOLDEN, "--batches",
+              str(batches), "-q", os.path.join(H.GOLDEN, "queries.fa"), "--match-dir", str(mdir),
+              "--filter-out", str(out), "-t", "0.7", "-n", "3", "--query-block-bases", "1000",
+              "--round-bytes", "500000"])
+    assert r.returncode == 0, r.stderr
+    for b in H.GOLDEN_BATCHES:
+        assert gzip.open(mdir / f"{b}____queries.gz", "rt").read() == H.golden_match_text(b, 3)
+    assert out.read_text() == H.golden_filter_fa(3)
