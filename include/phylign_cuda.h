@@ -151,7 +151,7 @@ void phy_merged_free(phy_merged* m);
 /* Merge candidates that come from the host (the `filter_queries.py -n N -q fa match files...`
  * entry: match files parsed by the driver): cands[offs[q] .. offs[q+1]) belong to query q;
  * score, batch_rank (<4096) and ref_rank (<2^20) form the sort key, doc is carried along.
- * Result via phy_merged_fetch.  Single GPU. */
+ * Result via phy_merged_fetch.  Local to this context (no collective). */
 int phy_merge_host(phy_ctx* ctx, uint32_t n_queries, uint32_t top_n, const uint64_t* offs,
                    const phy_cand* cands);
 

@@ -207,8 +207,30 @@ def _atomic_write(path, data: bytes, gz: bool):
             os.unlink(tmp)
 
 
+def _spawn_match_db_workers(a):
+    """`match-db --gpus N`: one worker process per GPU (device = rank), NCCL merge on rank 0."""
+    import subprocess
+    import tempfile
+    id_file = os.path.join(tempfile.mkdtemp(prefix="phylign_nccl_"), "id")
+    argv = [x for x in sys.argv[1:]]
+    procs = []
+    for r in range(a.gpus):
+        env = dict(os.environ, PHYLIGN_RANK=str(r), PHYLIGN_WORLD=str(a.gpus), PHYLIGN_NCCL_ID_FILE=id_file)
+        procs.append(subprocess.Popen([sys.executable, "-m", "phylign_b200.cli"] + argv, env=env))
+    rcs = [p.wait() for p in procs]
+    if any(rcs):
+        _die(f"match-db workers failed (exit codes {rcs})")
+
+
 def cmd_match_db(a):
-    from .matcher import Matcher
+    from .matcher import Matcher, nccl_unique_id
+    rank = int(os.environ.get("PHYLIGN_RANK", -1))
+    world = int(os.environ.get("PHYLIGN_WORLD", 1))
+    if a.gpus > 1 and rank < 0:
+        return _spawn_match_db_workers(a)
+    nccl = a.gpus > 1 and rank >= 0          # worker of a multi-GPU job: candidate lists meet over NCCL
+    if nccl and a.shard:
+        _die("--gpus and --shard are alternatives")
     with open(a.batches) as f:
         batches = sorted(filter(len, map(str.strip, f)))      # Snakefile:32-34
     records = fasta.read_cobs_records(a.q)
@@ -248,25 +270,40 @@ def cmd_match_db(a):
     n_shards, shard = 1, 0
     if a.shard:
         shard, n_shards = (int(x) for x in a.shard.split("/"))
+    if nccl:
+        shard, n_shards = rank, world
     budget = a.round_bytes or (int(a.hbm_budget * 0.9) if a.hbm_budget else 160 * 10 ** 9)
     plan = sharding.assign([shapes[b] for b in todo], n_shards, budget) if todo else sharding.Plan(n_shards)
     # 04_filter is merged from the device results of every round (no re-parsing of what was just
     # written); only match files that already existed (--resume) are parsed
-    want_filter = bool(a.filter_out) and n_shards == 1
-    if a.filter_out and n_shards != 1:
-        _die("--filter-out needs all batches: run `filter` over the match files of all shards instead")
-    queries, qid = _load_filter_queries(a.q) if want_filter else ({}, {})
+    want_filter = bool(a.filter_out) and (n_shards == 1 or nccl)
+    if a.filter_out and not want_filter:
+        _die("--filter-out needs all batches: use --gpus N, or run `filter` over the match files of all shards")
+    collect = want_filter and (not nccl or rank == 0)     # who assembles 04_filter
+    queries, qid = _load_filter_queries(a.q) if collect else ({}, {})
     brank = sharding.global_batch_ranks(batches)
-    rec2qid = np.array([qid[h.split(" ")[0]] for h, _ in records], dtype=np.int64) if want_filter else None
+    rec2qid = np.array([qid[h.split(" ")[0]] for h, _ in records], dtype=np.int64) if collect else None
     pieces, refs_by_rank = [], {}
-    if want_filter and merged_inputs:
+    if collect and merged_inputs:
         pieces, refs_by_rank = _parsed_pieces(merged_inputs, qid, brank, open(os.devnull, "w"))
-    with Matcher(a.device, a.hbm_budget) as m:
+    with Matcher(rank if nccl else a.device, a.hbm_budget) as m:
+        if nccl:                                              # rank 0 publishes the NCCL id through a file
+            id_file = os.environ["PHYLIGN_NCCL_ID_FILE"]
+            if rank == 0:
+                with open(id_file + ".tmp", "wb") as f:
+                    f.write(nccl_unique_id())
+                os.replace(id_file + ".tmp", id_file)
+            import time
+            for _ in range(6000):
+                if os.path.exists(id_file):
+                    break
+                time.sleep(0.05)
+            m.nccl_init(open(id_file, "rb").read(), rank, world)
         for rnd in plan.rounds:                               # resident round: load, match, write, evict
             mine = sorted(x.name for x in rnd[shard])
-            if not mine:
-                continue
-            loaded = m.load_indexes([path_of(b) for b in mine], mine, workers=a.load_workers)
+            if not mine and not (nccl and want_filter):
+                continue                                      # (under NCCL every rank joins every merge)
+            loaded = m.load_indexes([path_of(b) for b in mine], mine, workers=a.load_workers) if mine else []
             m.set_ranks(batches)
             texts = {idx: [] for idx in loaded}               # per index: one text piece per query block
             n_hit_queries = {idx: 0 for idx in loaded}
@@ -274,13 +311,14 @@ def cmd_match_db(a):
                 m.set_queries(block)
                 m.match_run(a.t, top_n=a.n, floor_mode=a.floor, merge_top_n=a.n if want_filter else 0)
                 res = m.fetch()
-                format_cobs_text_fast(block, res, m.indexes[loaded[0]], strip_prefix=True)   # warm the header cache
+                if loaded:
+                    format_cobs_text_fast(block, res, m.indexes[loaded[0]], strip_prefix=True)   # warm the header cache
                 with ThreadPoolExecutor(max_workers=max(1, a.load_workers)) as ex:   # C++ formatter releases the GIL
                     for idx, text in zip(loaded, ex.map(
                             lambda i: format_cobs_text_fast(block, res, m.indexes[i], strip_prefix=True), loaded)):
                         texts[idx].append(text)
                         n_hit_queries[idx] += len(res.units_of(idx))
-                if want_filter:                               # this block's top-N + ties per query and round
+                if collect:                                   # this block's top-N + ties per query and round
                     moffs, mc = m.merged()
                     q_of = q0 + np.repeat(np.arange(len(block), dtype=np.int64), np.diff(moffs.astype(np.int64)))
                     pieces.append((rec2qid[q_of], np.array(mc)))
@@ -297,7 +335,13 @@ def cmd_match_db(a):
                     refs_by_rank[ix.batch_rank] = [_ref_of(n) for n in ix.doc_names]
             for idx in loaded:
                 m.evict(idx)
-        if want_filter:
+        if collect and nccl:                                  # accessions of the batches other ranks hold
+            for b in todo:
+                if brank[b] not in refs_by_rank:
+                    st = IndexStream(path_of(b))
+                    refs_by_rank[brank[b]] = [_ref_of(n) for n in st.header.doc_names]
+                    st.abort()
+        if collect:
             fa = _final_merge(m, queries, pieces, refs_by_rank, a.n)
             os.makedirs(os.path.dirname(os.path.abspath(a.filter_out)), exist_ok=True)
             _atomic_write(a.filter_out, fa.encode(), gz=False)
@@ -386,6 +430,9 @@ def build_parser():
     d.add_argument("--load-workers", type=int, default=8, help="concurrent xz decoders while loading")
     d.add_argument("--query-block-bases", type=int, default=2 * 10 ** 9,
                    help="process the queries in blocks of at most this many bases (HBM for the hashes)")
+    d.add_argument("--gpus", type=int, default=1,
+                   help="N > 1: one worker process per GPU (devices 0..N-1), batches placed by the LPT plan, "
+                        "per-GPU candidate lists merged over NCCL on rank 0 (writes --filter-out directly)")
     d.add_argument("--bucket-dir", default=None,
                    help="also write {batch}____{qfile}.candidates.tsv (reference -> queries), the mapping "
                         "batch_align.py:126-171 derives per batch from the 04_filter FASTA")

@@ -571,15 +571,28 @@ extern "C" int phy_match_run(phy_ctx* ctx, const phy_match_params* p, uint32_t m
     }
     PHY_CUDA(ctx, cudaSetDevice(ctx->device));
     uint32_t k = 0, canon = 0, nh = 0;
-    PHY_TRY(resident_shape(ctx, &k, &canon, &nh, -1));
+    int n_active = 0;
+    for (auto& ix : ctx->idx) n_active += ix.alive && ix.committed && ix.active;
+    // a rank of a multi-GPU job may hold no index in some round: it still takes part in the merge
+    const bool empty_rank = n_active == 0 && ctx->n_ranks > 1;
+    if (!empty_rank) PHY_TRY(resident_shape(ctx, &k, &canon, &nh, -1));
     PHY_TRY(phy_sync_indexes(ctx));
     ctx->have_match = ctx->have_merged = false;
     ctx->hashes_valid = false;  // K1 is part of every match pass (never served from a cache)
     const uint64_t l0 = ctx->launches;
     PHY_CUDA(ctx, cudaEventRecord(ctx->ev_ph[0], ctx->stream));
-    PHY_TRY(prepare_hashes(ctx, k, canon, nh));
-    PHY_CUDA(ctx, cudaEventRecord(ctx->ev_ph[1], ctx->stream));
-    PHY_TRY(phy_launch_gather(ctx, p));
+    if (empty_rank) {
+        ctx->h_nk.assign((size_t)ctx->nq + 1, 0);
+        ctx->n_units = ctx->n_hits = 0;
+        ctx->units_ordered = true;
+        PHY_TRY(phy_ensure(ctx, ctx->d_qcount, ctx->nq + 1));
+        PHY_CUDA(ctx, cudaMemsetAsync(ctx->d_qcount.p, 0, ((size_t)ctx->nq + 1) * sizeof(uint32_t), ctx->stream));
+        PHY_CUDA(ctx, cudaEventRecord(ctx->ev_ph[1], ctx->stream));
+    } else {
+        PHY_TRY(prepare_hashes(ctx, k, canon, nh));
+        PHY_CUDA(ctx, cudaEventRecord(ctx->ev_ph[1], ctx->stream));
+        PHY_TRY(phy_launch_gather(ctx, p));
+    }
     PHY_CUDA(ctx, cudaEventRecord(ctx->ev_ph[2], ctx->stream));
     PHY_TRY(phy_launch_sort_units(ctx));
     ctx->merge_top_n = merge_top_n;
@@ -709,10 +722,6 @@ int phy_merge_host_impl(phy_ctx* ctx, uint32_t nq, uint32_t top_n, const uint64_
 extern "C" int phy_merge_host(phy_ctx* ctx, uint32_t n_queries, uint32_t top_n, const uint64_t* offs,
                               const phy_cand* cands) {
     if (!ctx || !offs || (!cands && offs[n_queries])) return PHY_ERR_ARG;
-    if (ctx->n_ranks > 1) {
-        phy_set_error(ctx, "phy_merge_host is a single-GPU entry point");
-        return PHY_ERR_STATE;
-    }
     for (uint32_t q = 0; q < n_queries; q++)
         if (offs[q + 1] < offs[q]) {
             phy_set_error(ctx, "candidate offsets must be non-decreasing");

@@ -62,3 +62,27 @@ def test_two_gpu_nccl_merge_equals_reference_filter(tmp_path, keep):
         _, e = p.communicate(timeout=300)
         assert p.returncode == 0, e[-3000:]
     assert out.read_text() == H.golden_filter_fa(keep)
+
+
+def test_match_db_gpus_2_writes_all_outputs(tmp_path):
+    """`match-db --gpus 2`: worker per GPU, NCCL merge, several rounds and query blocks (so one rank
+    sits out some merges with no index): match files and 04_filter equal the golden files."""
+    import ctypes as C
+    import gzip
+    from phylign_b200 import _lib
+    n = C.c_int()
+    _lib.load().phy_device_count(C.byref(n))
+    if n.value < 2:
+        pytest.skip("needs 2 GPUs")
+    batches = tmp_path / "batches.txt"
+    batches.write_text("\n".join(H.GOLDEN_BATCHES) + "\n")
+    mdir, out = tmp_path / "03_match", tmp_path / "04" / "q.fa"
+    r = subprocess.run([sys.executable, "-m", "phylign_b200.cli", "match-db", "--cobs-dir", H.GOLDEN, "--batches",
+                        str(batches), "-q", os.path.join(H.GOLDEN, "queries.fa"), "--match-dir", str(mdir),
+                        "--filter-out", str(out), "-t", "0.7", "-n", "3", "--gpus", "2", "--round-bytes", "500000",
+                        "--query-block-bases", "4000"], capture_output=True, text=True, cwd=ROOT,
+                       env=dict(os.environ, PYTHONPATH=ROOT), timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    for b in H.GOLDEN_BATCHES:
+        assert gzip.open(mdir / f"{b}____queries.gz", "rt").read() == H.golden_match_text(b, 3)
+    assert out.read_text() == H.golden_filter_fa(3)
