@@ -686,8 +686,12 @@ __device__ __forceinline__ uint32_t ring_accumulate(uint32_t (&pl)[P][4], uint32
 #ifndef PHY_RING_MINBLOCKS
 #define PHY_RING_MINBLOCKS 1
 #endif
+#ifndef PHY_RING_MINBLOCKS_SHORT
+#define PHY_RING_MINBLOCKS_SHORT 1
+#endif
 template <int LPR, int P, int NB, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, PHY_RING_MINBLOCKS) gather_count_ring_kernel(const GatherArgs a) {
+__global__ void __launch_bounds__(WARPS * 32, (P <= 8 ? PHY_RING_MINBLOCKS_SHORT : PHY_RING_MINBLOCKS))
+gather_count_ring_kernel(const GatherArgs a) {
     constexpr int G = 32 / LPR;
     extern __shared__ __align__(128) uint8_t smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
