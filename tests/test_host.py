@@ -282,3 +282,47 @@ def test_query_blocks_partition():
     assert all(sum(len(s) for _, s in b) <= 20 or len(b) == 1 for _, b in blocks)
     assert list(query_blocks(recs, 10 ** 9)) == [(0, recs)]
     assert list(query_blocks([], 5)) == [(0, [])]
+
+
+def test_header_roundtrip_property():
+    """ClassicHeader.to_bytes / read_header round trip on random headers (hypothesis), including
+    bodies whose first bytes look like a name table, and chunked/pipe-like reads."""
+    import io
+    from hypothesis import given, settings, strategies as st
+    from phylign_b200.cobs_index import ClassicHeader, IndexFormatError, parse_bytes, read_header
+
+    name = st.text(alphabet="ABCDEFGHIJKLMNOPQRSTUVWXYZ0123456789_.-", min_size=1, max_size=24)
+
+    class Dribble(io.RawIOBase):          # a pipe that hands out at most 7 bytes per read
+        def __init__(self, b):
+            self.b, self.p = b, 0
+
+        def readable(self):
+            return True
+
+        def read(self, n=-1):
+            n = 7 if n < 0 else min(n, 7)
+            out = self.b[self.p:self.p + n]
+            self.p += len(out)
+            return out
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(name, min_size=1, max_size=40), st.integers(1, 31), st.integers(0, 1), st.integers(1, 50),
+           st.integers(1, 4), st.binary(min_size=0, max_size=3))
+    def check(names, k, canon, sig, nh, junk):
+        hdr = ClassicHeader(k, canon, len(names), sig, nh, names)
+        body = (b"\nCLASSIC_INDEX\n" * 50 + junk)[:hdr.body_size].ljust(hdr.body_size, b"\x55")
+        raw = hdr.to_bytes() + body
+        h2, b2 = parse_bytes(raw)
+        assert (h2.term_size, h2.canonicalize, h2.n_docs, h2.signature_size, h2.num_hashes, h2.doc_names) == \
+            (k, canon, len(names), sig, nh, names)
+        assert b2 == body and h2.header_size == len(hdr.to_bytes())
+        h3 = read_header(Dribble(raw))
+        assert h3.doc_names == names and h3.header_size == h2.header_size
+        try:
+            parse_bytes(raw + b"x")
+            assert False, "oversized body accepted"
+        except IndexFormatError:
+            pass
+
+    check()
