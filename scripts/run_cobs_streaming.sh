@@ -1,14 +1,10 @@
-#!/usr/bin/env bash
-# Drop-in for the reference's scripts/run_cobs_streaming.sh (same 5 positionals, same stdout):
-# the index is decompressed on the host, queried on the B200.  No CPU fallback.
-set -e
-set -o pipefail
-set -u
-
-readonly PROGNAME=$(basename "$0")
-readonly REPO=$(cd "$(dirname "$0")/.." && pwd)
-if [[ $# -ne 5 ]]; then
-	>&2 echo "usage: $PROGNAME kmer_thres threads cobs_index.xz uncompressed_size query.fa"
+#!/bin/sh
+# GPU drop-in with the calling convention of Phylign's run_cobs_streaming.sh: five positionals in,
+# `cobs query` text on stdout.  The xz stream is decoded on the host, the query runs on the B200
+# (python -m phylign_b200.cli run-cobs-streaming); there is no CPU fallback.
+[ "$#" -eq 5 ] || {
+	echo "usage: $(basename -- "$0") kmer_thres threads cobs_index.xz uncompressed_size query.fa" >&2
 	exit 1
-fi
-PYTHONPATH="${REPO}${PYTHONPATH:+:$PYTHONPATH}" exec python3 -m phylign_b200.cli run-cobs-streaming "$1" "$2" "$3" "$4" "$5"
+}
+repo=$(CDPATH= cd -- "$(dirname -- "$0")/.." && pwd) || exit 1
+PYTHONPATH="$repo${PYTHONPATH:+:$PYTHONPATH}" exec python3 -m phylign_b200.cli run-cobs-streaming "$@"
