@@ -172,6 +172,22 @@ int phy_format_filter_fasta(const phy_merged* m, const char* qnames, const uint6
                             const char* const* ref_names, const uint64_t* const* ref_offs,
                             const uint32_t* ref_counts, char** out, uint64_t* out_len);
 void phy_text_free(char* p);
+/* Parser of a (decompressed) match file with the rules of filter_queries.py:27-66 (`cobs_iterator`):
+ * per block the query name (offset/length into `text`) and its hits [first_hit[b], first_hit[b+1]);
+ * per hit the accession (text after the single '_' of the name) and the k-mer count.  Host only.
+ * Malformed input (hit before a header, a name without exactly one '_', non-integer counts, empty
+ * file) returns PHY_ERR_ARG -- the reference raises on the same inputs. */
+typedef struct phy_match_text {
+    uint64_t n_blocks, n_hits;
+    uint64_t* q_off;      /* [n_blocks] */
+    uint32_t* q_len;      /* [n_blocks] */
+    uint64_t* first_hit;  /* [n_blocks+1] */
+    uint64_t* ref_off;    /* [n_hits] */
+    uint32_t* ref_len;    /* [n_hits] */
+    uint32_t* kmers;      /* [n_hits] */
+} phy_match_text;
+int phy_parse_match_text(const char* text, uint64_t len, phy_match_text** out);
+void phy_match_text_free(phy_match_text* r);
 
 /* ------------------------------------------------------------------- multi-GPU */
 #define PHY_NCCL_ID_BYTES 128

@@ -53,6 +53,13 @@ class Merged(C.Structure):
                 ("cands", C.POINTER(Cand)), ("d2h_bytes", C.c_uint64)]
 
 
+class MatchText(C.Structure):
+    _fields_ = [("n_blocks", C.c_uint64), ("n_hits", C.c_uint64), ("q_off", C.POINTER(C.c_uint64)),
+                ("q_len", C.POINTER(C.c_uint32)), ("first_hit", C.POINTER(C.c_uint64)),
+                ("ref_off", C.POINTER(C.c_uint64)), ("ref_len", C.POINTER(C.c_uint32)),
+                ("kmers", C.POINTER(C.c_uint32))]
+
+
 class IndexInfo(C.Structure):
     _fields_ = [("signature_size", C.c_uint64), ("num_hashes", C.c_uint64), ("hbm_bytes", C.c_uint64),
                 ("term_size", C.c_uint32), ("n_docs", C.c_uint32), ("row_size", C.c_uint32),
@@ -100,6 +107,8 @@ PROTOTYPES = {
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p),
                                          C.POINTER(C.c_uint64)]),
     "phy_text_free": (None, [C.c_void_p]),
+    "phy_parse_match_text": (C.c_int, [C.c_char_p, C.c_uint64, C.POINTER(C.POINTER(MatchText))]),
+    "phy_match_text_free": (None, [C.POINTER(MatchText)]),
     "phy_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "phy_nccl_init": (C.c_int, [_P, C.c_void_p, C.c_int, C.c_int]),
     "phy_timer_start": (C.c_int, [_P]),

@@ -129,6 +129,46 @@ def parse_match_file(path):
     return blocks
 
 
+def parse_match_file_native(path):
+    """Same content as parse_match_file, produced by the library's C++ parser, as arrays:
+    (qnames [str per block], first_hit uint64[n_blocks+1], ref_ids int64[n_hits], refs_sorted [str],
+    kmers uint32[n_hits]); ref_ids index refs_sorted (byte order = Python str order for ASCII)."""
+    import ctypes as C
+    from . import _lib
+    L = _lib.load()
+    opener = gzip.open if str(path).endswith(".gz") else open
+    with opener(path, "rb") as f:
+        text = f.read()
+    mp = C.POINTER(_lib.MatchText)()
+    rc = L.phy_parse_match_text(text, len(text), C.byref(mp))
+    if rc != 0:
+        raise ValueError(f"{path}: {L.phy_last_error(None).decode()}")
+    try:
+        m = mp.contents
+        nb, nh = int(m.n_blocks), int(m.n_hits)
+        arr = lambda p, n, dt: np.ctypeslib.as_array(p, shape=(n,)).astype(dt, copy=True) if n else np.zeros(0, dt)
+        q_off, q_len = arr(m.q_off, nb, np.int64), arr(m.q_len, nb, np.int64)
+        first_hit = arr(m.first_hit, nb + 1, np.uint64)
+        ref_off, ref_len = arr(m.ref_off, nh, np.int64), arr(m.ref_len, nh, np.int64)
+        kmers = arr(m.kmers, nh, np.uint32)
+    finally:
+        L.phy_match_text_free(mp)
+    qnames = [text[o:o + n].decode() for o, n in zip(q_off.tolist(), q_len.tolist())]
+    if nh:
+        width = int(ref_len.max())
+        buf = np.frombuffer(text, dtype=np.uint8)
+        cols = np.arange(width, dtype=np.int64)
+        idx = np.minimum(ref_off[:, None] + cols[None, :], len(buf) - 1)
+        mat = np.where(cols[None, :] < ref_len[:, None], buf[idx], 0).astype(np.uint8)
+        names = np.ascontiguousarray(mat).view(f"S{width}").ravel()     # NUL padded fixed-width strings
+        uniq, inv = np.unique(names, return_inverse=True)
+        refs_sorted = [u.decode() for u in uniq.tolist()]
+        ref_ids = inv.astype(np.int64)
+    else:
+        refs_sorted, ref_ids = [], np.zeros(0, np.int64)
+    return qnames, first_hit, ref_ids, refs_sorted, kmers
+
+
 def _load_filter_queries(query_fn):
     """(ordered {qname: seq}, {qname: position}) the way filter_queries.py:163-176 builds its dict."""
     queries = {}
@@ -138,26 +178,31 @@ def _load_filter_queries(query_fn):
 
 
 def _parsed_pieces(match_fns, qid, brank, log):
-    """Candidates of already written match files: [(qid array, CAND array)], {batch_rank: refs}."""
+    """Candidates of already written match files: [(qid array, CAND array)], {batch_rank: refs}.
+    Files are parsed natively (phy_parse_match_text); several files of one batch are allowed."""
     from .matcher import CAND_DT
-    pieces, refs_by_rank = [], {}
     by_batch = {}
     for fn in match_fns:
         batch = os.path.basename(fn).split("____")[0]
         print(f"Translating matches {fn}", file=log)
-        by_batch.setdefault(batch, []).extend(parse_match_file(fn))
-    for batch, blocks in by_batch.items():
-        refs = sorted({ref for _, hits in blocks for ref, _ in hits})
-        rr = {r: i for i, r in enumerate(refs)}
+        by_batch.setdefault(batch, []).append(parse_match_file_native(fn))
+    pieces, refs_by_rank = [], {}
+    for batch, parsed in by_batch.items():
         br = brank[batch]
+        refs = sorted({r for p in parsed for r in p[3]})          # accessions of the batch, str order
+        rr = {r: i for i, r in enumerate(refs)}
         refs_by_rank[br] = refs
-        qs, rows = [], []
-        for qname, hits in blocks:
-            if qname not in qid:
-                raise KeyError(f"query {qname!r} of batch {batch} is not in the query file")
-            qs.extend([qid[qname]] * len(hits))
-            rows.extend((k, br, rr[ref], rr[ref]) for ref, k in hits)
-        pieces.append((np.array(qs, dtype=np.int64), np.array(rows, dtype=CAND_DT) if rows else np.zeros(0, CAND_DT)))
+        for qnames, first_hit, ref_ids, refs_sorted, kmers in parsed:
+            try:
+                q_of_block = np.array([qid[q] for q in qnames], dtype=np.int64)
+            except KeyError as e:
+                raise KeyError(f"query {e.args[0]!r} of batch {batch} is not in the query file") from None
+            remap = np.array([rr[r] for r in refs_sorted], dtype=np.int64)   # file-local id -> batch rank
+            rank = remap[ref_ids] if len(ref_ids) else np.zeros(0, np.int64)
+            c = np.zeros(len(kmers), dtype=CAND_DT)
+            c["score"], c["batch_rank"], c["doc"], c["ref_rank"] = kmers, br, rank, rank
+            counts = np.diff(first_hit.astype(np.int64))
+            pieces.append((np.repeat(q_of_block, counts), c))
     return pieces, refs_by_rank
 
 

@@ -102,3 +102,121 @@ extern "C" int phy_format_filter_fasta(const phy_merged* m, const char* qnames, 
 }
 
 extern "C" void phy_text_free(char* p) { free(p); }
+
+// ---- parser of match files (the reading side of the same protocol) -----------------------------
+// Restates the rules of /root/reference/scripts/filter_queries.py:27-66 (`cobs_iterator`) natively:
+// lines are stripped, empty lines skipped; "*<qname>[ comment]\t<int>" opens a block (qname = text up
+// to the first space or tab); a hit line is "<name><ws><kmers>" with exactly two whitespace-separated
+// fields, and <name> holds exactly ONE '_' (`rid, ref = tmp_name.split("_")`): ref = text after it.
+namespace {
+struct MatchText {
+    std::vector<uint64_t> q_off, first_hit, ref_off;
+    std::vector<uint32_t> q_len, ref_len, kmers;
+};
+inline bool is_ws(char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\v' || c == '\f'; }
+}  // namespace
+
+extern "C" int phy_parse_match_text(const char* text, uint64_t len, phy_match_text** out) {
+    if (!text || !out) return PHY_ERR_ARG;
+    *out = nullptr;
+    MatchText m;
+    uint64_t line_no = 0, p = 0;
+    while (p < len) {
+        uint64_t e = p;
+        while (e < len && text[e] != '\n') e++;
+        uint64_t a = p, b = e;  // strip
+        while (a < b && is_ws(text[a])) a++;
+        while (b > a && is_ws(text[b - 1])) b--;
+        p = e + 1;
+        line_no++;
+        if (a == b) continue;
+        if (text[a] == '*') {
+            uint64_t tab = a + 1;
+            while (tab < b && text[tab] != '\t') tab++;
+            if (tab == b) {
+                phy_set_error(nullptr, "match file line %llu: header without a tab-separated count", (unsigned long long)line_no);
+                return PHY_ERR_ARG;
+            }
+            uint64_t c = tab + 1;
+            if (c == b) { phy_set_error(nullptr, "match file line %llu: empty count", (unsigned long long)line_no); return PHY_ERR_ARG; }
+            uint64_t c2 = c;
+            while (c2 < b && text[c2] != '\t') c2++;      // parts[1] of x[1:].split("\t")
+            for (uint64_t i = c; i < c2; i++)
+                if (text[i] < '0' || text[i] > '9') {
+                    phy_set_error(nullptr, "match file line %llu: count is not an integer", (unsigned long long)line_no);
+                    return PHY_ERR_ARG;
+                }
+            uint64_t qe = a + 1;
+            while (qe < tab && text[qe] != ' ') qe++;   // qname = parts[0].split(" ")[0]
+            m.q_off.push_back(a + 1);
+            m.q_len.push_back((uint32_t)(qe - (a + 1)));
+            m.first_hit.push_back(m.kmers.size());
+        } else {
+            if (m.q_off.empty()) {
+                phy_set_error(nullptr, "match file line %llu: hit line before any query header", (unsigned long long)line_no);
+                return PHY_ERR_ARG;
+            }
+            // exactly two whitespace-separated fields
+            uint64_t n1 = a;
+            while (n1 < b && !is_ws(text[n1])) n1++;
+            uint64_t k0 = n1;
+            while (k0 < b && is_ws(text[k0])) k0++;
+            uint64_t k1 = k0;
+            while (k1 < b && !is_ws(text[k1])) k1++;
+            if (n1 == b || k0 == b || k1 != b) {
+                phy_set_error(nullptr, "match file line %llu: expected '<name> <kmers>'", (unsigned long long)line_no);
+                return PHY_ERR_ARG;
+            }
+            uint64_t us = a, n_us = 0, first_us = 0;
+            for (; us < n1; us++)
+                if (text[us] == '_') { if (!n_us) first_us = us; n_us++; }
+            if (n_us != 1) {
+                phy_set_error(nullptr, "match file line %llu: reference name must hold exactly one '_'", (unsigned long long)line_no);
+                return PHY_ERR_ARG;
+            }
+            uint64_t v = 0;
+            for (uint64_t i = k0; i < k1; i++) {
+                if (text[i] < '0' || text[i] > '9' || v > 0xFFFFFFFFull) {
+                    phy_set_error(nullptr, "match file line %llu: k-mer count is not an integer", (unsigned long long)line_no);
+                    return PHY_ERR_ARG;
+                }
+                v = v * 10 + (uint64_t)(text[i] - '0');
+            }
+            m.ref_off.push_back(first_us + 1);
+            m.ref_len.push_back((uint32_t)(n1 - first_us - 1));
+            m.kmers.push_back((uint32_t)std::min<uint64_t>(v, 0xFFFFFFFFull));
+        }
+    }
+    if (m.q_off.empty()) {
+        phy_set_error(nullptr, "empty match file");
+        return PHY_ERR_ARG;
+    }
+    m.first_hit.push_back(m.kmers.size());
+    phy_match_text* r = (phy_match_text*)calloc(1, sizeof(phy_match_text));
+    if (!r) return PHY_ERR_NOMEM;
+    r->n_blocks = m.q_off.size();
+    r->n_hits = m.kmers.size();
+    auto dup = [](const void* src, size_t bytes) -> void* {
+        void* p = malloc(bytes ? bytes : 1);
+        if (p && bytes) memcpy(p, src, bytes);
+        return p;
+    };
+    r->q_off = (uint64_t*)dup(m.q_off.data(), m.q_off.size() * 8);
+    r->q_len = (uint32_t*)dup(m.q_len.data(), m.q_len.size() * 4);
+    r->first_hit = (uint64_t*)dup(m.first_hit.data(), m.first_hit.size() * 8);
+    r->ref_off = (uint64_t*)dup(m.ref_off.data(), m.ref_off.size() * 8);
+    r->ref_len = (uint32_t*)dup(m.ref_len.data(), m.ref_len.size() * 4);
+    r->kmers = (uint32_t*)dup(m.kmers.data(), m.kmers.size() * 4);
+    if (!r->q_off || !r->q_len || !r->first_hit || !r->ref_off || !r->ref_len || !r->kmers) {
+        phy_match_text_free(r);
+        return PHY_ERR_NOMEM;
+    }
+    *out = r;
+    return PHY_OK;
+}
+
+extern "C" void phy_match_text_free(phy_match_text* r) {
+    if (!r) return;
+    free(r->q_off); free(r->q_len); free(r->first_hit); free(r->ref_off); free(r->ref_len); free(r->kmers);
+    free(r);
+}

@@ -326,3 +326,34 @@ def test_header_roundtrip_property():
             pass
 
     check()
+
+
+def test_native_match_file_parser_equals_python_parser(tmp_path):
+    """phy_parse_match_text (C++) == the line-by-line Python restatement of filter_queries.py:27-66,
+    on the golden match files and on malformed inputs (same inputs rejected)."""
+    from phylign_b200.cli import parse_match_file, parse_match_file_native
+    for keep in (1, 3, 100):
+        for b in H.GOLDEN_BATCHES:
+            p = os.path.join(H.GOLDEN, f"n{keep}", f"{b}____queries.gz")
+            want = parse_match_file(p)
+            qnames, first_hit, ref_ids, refs_sorted, kmers = parse_match_file_native(p)
+            assert qnames == [q for q, _ in want]
+            got = [[(refs_sorted[int(r)], int(k)) for r, k in zip(ref_ids[int(a):int(z)], kmers[int(a):int(z)])]
+                   for a, z in zip(first_hit[:-1], first_hit[1:])]
+            assert got == [hits for _, hits in want]
+            assert refs_sorted == sorted(refs_sorted)
+    cases = {"hit_first": "a_b\t3\n", "two_underscores": "*q\t1\na_b_c\t3\n", "no_underscore": "*q\t1\nabc\t3\n",
+             "three_fields": "*q\t1\na_b\t3\t4\n", "no_tab_header": "*q 1\n", "bad_count": "*q\tx\n",
+             "bad_kmers": "*q\t1\na_b\tx\n", "empty": "\n\n"}
+    for name, text in cases.items():
+        p = tmp_path / f"{name}__01____q.txt"
+        p.write_text(text)
+        with pytest.raises(Exception):
+            parse_match_file(str(p))
+        with pytest.raises(ValueError):
+            parse_match_file_native(str(p))
+    ok = tmp_path / "ok__01____q.txt"
+    ok.write_text("\n*q1 some comment\t2  \n  x_R1 \t 5\r\ny_R0\t4\n\n*q2\t0\n")
+    assert parse_match_file(str(ok)) == [("q1", [("R1", 5), ("R0", 4)]), ("q2", [])]
+    qn, fh, ri, rs, km = parse_match_file_native(str(ok))
+    assert qn == ["q1", "q2"] and fh.tolist() == [0, 2, 2] and [rs[i] for i in ri] == ["R1", "R0"] and km.tolist() == [5, 4]
