@@ -3,7 +3,7 @@
 random document counts / signature sizes / hash counts / k / canonical flag, query lengths across
 every kernel class boundary, random thresholds and top-N.  Usage: fuzz_parity.py [cases] [seed]"""
 import os, random, sys, tempfile
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # repo root
 import numpy as np
 import oracle
 from phylign_b200.matcher import Matcher
