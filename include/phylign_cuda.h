@@ -33,6 +33,7 @@ extern "C" {
 #define PHY_ERR_STATE (-4)  /* call out of order (e.g. match before queries) */
 #define PHY_ERR_NCCL (-5)   /* NCCL failure / libnccl not loadable */
 #define PHY_ERR_QUERY (-6)  /* query holds a letter outside ACGT (cobs aborts too) */
+#define PHY_ERR_IO (-7)     /* file could not be created / written / renamed */
 
 #define PHY_ABI_VERSION 1
 
@@ -189,6 +190,34 @@ typedef struct phy_match_text {
 int phy_parse_match_text(const char* text, uint64_t len, phy_match_text** out);
 void phy_match_text_free(phy_match_text* r);
 
+/* -------------------------------------------------------------- match-file writer
+ * The tail of the reference's per-batch pipeline, `... | postprocess_cobs.py -n N | gzip --fast >
+ * intermediate/03_match/{batch}____{qfile}.gz` (Snakefile:425-427,467-469,482-484), for the results of
+ * one query block and any number of indexes at once: formatted and deflated (zlib, level 1 = --fast)
+ * on n_threads host threads, one gzip member per (file, query range), appended in query order.
+ * Host only (no GPU work), callable from a thread other than the one driving the ctx.
+ * A phy_mfile is written as <final_path>.tmp.<pid> and renamed by phy_mfile_commit: nothing partial
+ * is ever visible at the output path.  gzip_level 0 writes plain text. */
+typedef struct phy_mfile phy_mfile;
+int phy_mfile_open(const char* final_path, int gzip_level, phy_mfile** out);
+int phy_mfile_commit(phy_mfile* f, uint64_t* file_bytes /* may be NULL */);
+void phy_mfile_abort(phy_mfile* f);
+typedef struct phy_mfile_job {
+    phy_mfile* file;
+    uint32_t idx_id;          /* units of this index go to `file` */
+    uint32_t n_docs;
+    const char* names;        /* document names of the index, concatenated */
+    const uint64_t* noffs;    /* [n_docs+1] */
+} phy_mfile_job;
+typedef struct phy_write_stats {   /* accumulated (+=) over calls; *_s are thread-seconds except wall_s */
+    double format_s, deflate_s, write_s, wall_s;
+    uint64_t text_bytes, file_bytes, n_header_lines, n_hit_lines;
+} phy_write_stats;
+/* headers/hoffs/skip/strip_prefix as in phy_format_cobs_text */
+int phy_write_match_blocks(const phy_results* r, const phy_mfile_job* jobs, uint32_t n_jobs,
+                           const char* headers, const uint64_t* hoffs, const uint8_t* skip,
+                           int strip_prefix, int n_threads, phy_write_stats* stats /* may be NULL */);
+
 /* ------------------------------------------------------------------- multi-GPU */
 #define PHY_NCCL_ID_BYTES 128
 int phy_nccl_unique_id(void* id_out /* PHY_NCCL_ID_BYTES */);
@@ -205,6 +234,10 @@ int phy_last_phase_ms(phy_ctx* ctx, float out[4]);
 /* index-row bytes (file row size, not stride) the fused ring kernel really gathered in the last
  * phy_match_run: < sum K*row_size when threshold pruning ended units early */
 int phy_last_gather_bytes(phy_ctx* ctx, uint64_t* bytes);
+/* the same per index (per-batch log lines: rows read / all rows) */
+int phy_last_gather_bytes_of(phy_ctx* ctx, int idx_id, uint64_t* bytes);
+/* HBM accounting of this context: bytes it may use in total / bytes in use now */
+int phy_ctx_budget(phy_ctx* ctx, uint64_t* budget, uint64_t* used);
 /* tuning / A-B switches: "prune" 0|1 (exact threshold pruning, default 1),
  * "kernel_path" 1|2|3 (register-staged | bulk-copy ring | cp.async ring, default 3) */
 int phy_ctx_set_option(phy_ctx* ctx, const char* name, int64_t value);

@@ -19,13 +19,57 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
 CLI_PATH = os.path.join(_HERE, "_build", "cobs_oracle")
+NATIVE_LIB_PATH = os.path.join(_HERE, "_build", "native", "liboracle.so")
+NATIVE_CLI_PATH = os.path.join(_HERE, "_build", "native", "cobs_oracle")
+_use_native = False
+
+
+def _stale(*outs) -> bool:
+    srcs = [os.path.join(_HERE, f) for f in ("cobs_oracle.c", "cobs_oracle.h", "cobs_oracle_cli.c", "Makefile")]
+    if not all(os.path.exists(o) for o in outs):
+        return True
+    t = min(os.path.getmtime(o) for o in outs)
+    return any(os.path.getmtime(x) > t for x in srcs)
 
 
 def build(force: bool = False) -> None:
-    """Compile the oracle with gcc (seconds)."""
-    if force or not (os.path.exists(LIB_PATH) and os.path.exists(CLI_PATH)):
+    """Compile the oracle with gcc (seconds): the portable build the tests use."""
+    if force or _stale(LIB_PATH, CLI_PATH):
         subprocess.check_call(["make", "-C", _HERE] + (["-B"] if force else []),
                               stdout=subprocess.DEVNULL)
+
+
+def _cpu_id() -> str:
+    import hashlib
+    try:
+        txt = open("/proc/cpuinfo").read()
+        keep = [l for l in txt.splitlines() if l.startswith(("model name", "flags"))][:2]
+        return hashlib.sha1("\n".join(keep).encode()).hexdigest()
+    except Exception:
+        return "unknown"
+
+
+def build_native(force: bool = False) -> bool:
+    """-O3 -march=native build for the CPU timing legs of bench.py, compiled on the machine that
+    runs it (never shipped between machines).  Must be called before the first lib() use.
+    Returns False (and stays on the portable build) when gcc is missing."""
+    global _use_native
+    try:
+        stamp = os.path.join(_HERE, "_build", "native", ".cpu")
+        cpu = _cpu_id()
+        same_cpu = os.path.exists(stamp) and open(stamp).read() == cpu     # -march=native is per machine
+        if force or not same_cpu or _stale(NATIVE_LIB_PATH, NATIVE_CLI_PATH):
+            subprocess.check_call(["make", "-C", _HERE, "-B", "native"], stdout=subprocess.DEVNULL)
+            with open(stamp, "w") as f:
+                f.write(cpu)
+        _use_native = _lib is None
+    except Exception:
+        _use_native = False
+    return _use_native
+
+
+def cli_path() -> str:
+    return NATIVE_CLI_PATH if _use_native else CLI_PATH
 
 
 class _Index(C.Structure):
@@ -48,8 +92,12 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        build()
-        L = C.CDLL(LIB_PATH)
+        if not _use_native:
+            build()
+        L = C.CDLL(NATIVE_LIB_PATH if _use_native else LIB_PATH)
+        L.orc_simd_mode.restype = C.c_int
+        L.orc_set_simd_mode.restype = C.c_int
+        L.orc_set_simd_mode.argtypes = [C.c_int]
         L.orc_xxh64.restype = C.c_uint64
         L.orc_xxh64.argtypes = [C.c_char_p, C.c_size_t, C.c_uint64]
         L.orc_canonical.restype = C.c_int
@@ -89,6 +137,11 @@ def lib():
                                      C.c_uint32, C.c_uint32, C.c_uint32, C.c_char_p]
         _lib = L
     return _lib
+
+
+def set_simd(avx2: bool) -> str:
+    """Counting kernel of the sliced path: "sse2" (cobs 0.2.1 shape) or "avx2"; returns what is in effect."""
+    return "avx2" if lib().orc_set_simd_mode(int(bool(avx2))) else "sse2"
 
 
 def xxh64(data: bytes, seed: int = 0) -> int:

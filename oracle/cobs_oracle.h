@@ -90,6 +90,10 @@ uint32_t orc_select(const uint32_t* scores, uint32_t n_docs, uint32_t min_score,
  * mode 1: queries spread over n_threads (scalar per-query path).
  * Writes per-query n_pass into n_pass[nq] (may be NULL) and returns total
  * number of passing (query,doc) pairs, or -1 on error. */
+/* counting kernel: 0 = SSE2 byte-expansion adds (the cobs 0.2.1 shape, default), 1 = the same with
+ * 256-bit adds (needs AVX2; refused otherwise).  ORC_SIMD=avx2 in the environment selects 1. */
+int orc_simd_mode(void);
+int orc_set_simd_mode(int avx2);
 int64_t orc_query_batch(const orc_index* idx, const char* seqs, const uint64_t* offs,
                         uint32_t nq, double threshold, int floor_mode, int n_threads,
                         int mode, uint32_t* n_pass);

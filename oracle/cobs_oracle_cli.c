@@ -2,7 +2,7 @@
  * cobs_oracle_cli.c -- CPU ORACLE command line (test infrastructure, NOT product).
  *
  *   cobs_oracle query [--load-complete] -t THR -T THREADS -i INDEX
- *                     [--index-sizes N] -f QUERY.fa [--floor]
+ *                     [--index-sizes N] -f QUERY.fa [--floor] [--threads-over-slices] [--avx2]
  *       restates the `cobs query` call of
  *       /root/reference/scripts/run_cobs_streaming.sh:24-29: prints, per FASTA
  *       record, "*<header minus first char>\t<n>\n" followed by n lines
@@ -59,7 +59,7 @@ static rec_t* read_fasta(const char* path, size_t* n_out) {
 
 static int cmd_query(int argc, char** argv) {
     const char* index = NULL; const char* qfile = NULL;
-    double thr = 0.8; int threads = 1, floor_mode = 0;
+    double thr = 0.8; int threads = 1, floor_mode = 0, over_slices = 0;
     for (int i = 0; i < argc; i++) {
         if (!strcmp(argv[i], "-t") && i + 1 < argc) thr = strtod(argv[++i], NULL);
         else if (!strcmp(argv[i], "-T") && i + 1 < argc) threads = atoi(argv[++i]);
@@ -68,6 +68,8 @@ static int cmd_query(int argc, char** argv) {
         else if (!strcmp(argv[i], "--index-sizes") && i + 1 < argc) ++i;
         else if (!strcmp(argv[i], "--load-complete")) {}
         else if (!strcmp(argv[i], "--floor")) floor_mode = 1;
+        else if (!strcmp(argv[i], "--threads-over-slices")) over_slices = 1;   /* the cobs thread layout */
+        else if (!strcmp(argv[i], "--avx2")) orc_set_simd_mode(1);
         else { fprintf(stderr, "unknown argument %s\n", argv[i]); return 1; }
     }
     if (!index || !qfile) { fprintf(stderr, "query: -i and -f required\n"); return 1; }
@@ -75,6 +77,44 @@ static int cmd_query(int argc, char** argv) {
     if (!idx) { fprintf(stderr, "cannot read index %s\n", index); return 1; }
     size_t nq; rec_t* recs = read_fasta(qfile, &nq);
     if (!recs && nq) { fprintf(stderr, "cannot read %s\n", qfile); return 1; }
+    if (threads > 1 && !over_slices) {
+        /* queries over threads (the faster layout for many short queries), output kept in file
+         * order: blocks of queries are scored in parallel into per-query text buffers */
+        const size_t BLOCK = 2048;
+        char** txt = (char**)calloc(BLOCK, sizeof(char*));
+        size_t* tlen = (size_t*)calloc(BLOCK, sizeof(size_t));
+        int bad = 0;
+        for (size_t q0 = 0; q0 < nq && !bad; q0 += BLOCK) {
+            size_t n = nq - q0 < BLOCK ? nq - q0 : BLOCK;
+#pragma omp parallel num_threads(threads)
+            {
+                uint32_t* sc = (uint32_t*)malloc(sizeof(uint32_t) * (idx->n_docs + 1));
+                orc_hit* hh = (orc_hit*)malloc(sizeof(orc_hit) * (idx->n_docs + 1));
+#pragma omp for schedule(dynamic, 8)
+                for (long i = 0; i < (long)n; i++) {
+                    rec_t* r = &recs[q0 + (size_t)i];
+                    txt[i] = NULL; tlen[i] = 0;
+                    if (r->len == 0) continue;
+                    int64_t K = orc_query_scores_sliced(idx, r->seq, r->len, sc, 1);
+                    if (K < 0) { bad = 1; continue; }
+                    uint32_t cnt = 0;
+                    if (K > 0) cnt = orc_select(sc, idx->n_docs, orc_threshold_terms(thr, (uint32_t)K, floor_mode), hh);
+                    size_t cap = strlen(r->name) + 32;
+                    for (uint32_t j = 0; j < cnt; j++) cap += strlen(idx->doc_names[hh[j].doc]) + 16;
+                    char* b = (char*)malloc(cap);
+                    size_t w = (size_t)sprintf(b, "*%s\t%u\n", r->name, cnt);
+                    for (uint32_t j = 0; j < cnt; j++)
+                        w += (size_t)sprintf(b + w, "%s\t%u\n", idx->doc_names[hh[j].doc], hh[j].score);
+                    txt[i] = b; tlen[i] = w;
+                }
+                free(sc); free(hh);
+            }
+            for (size_t i = 0; i < n; i++)
+                if (txt[i]) { fwrite(txt[i], 1, tlen[i], stdout); free(txt[i]); }
+        }
+        if (bad) { fprintf(stderr, "invalid letter in a query\n"); return 1; }
+        return 0;
+    }
     uint32_t* scores = (uint32_t*)malloc(sizeof(uint32_t) * (idx->n_docs + 1));
     orc_hit* hits = (orc_hit*)malloc(sizeof(orc_hit) * (idx->n_docs + 1));
     for (size_t q = 0; q < nq; q++) {

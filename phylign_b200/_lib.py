@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(HERE, "libphylign_cuda.so")
 
 PHY_OK = 0
 ERR_NAMES = {-1: "PHY_ERR_CUDA", -2: "PHY_ERR_ARG", -3: "PHY_ERR_NOMEM", -4: "PHY_ERR_STATE",
-             -5: "PHY_ERR_NCCL", -6: "PHY_ERR_QUERY"}
+             -5: "PHY_ERR_NCCL", -6: "PHY_ERR_QUERY", -7: "PHY_ERR_IO"}
 NCCL_ID_BYTES = 128
 
 
@@ -58,6 +58,17 @@ class MatchText(C.Structure):
                 ("q_len", C.POINTER(C.c_uint32)), ("first_hit", C.POINTER(C.c_uint64)),
                 ("ref_off", C.POINTER(C.c_uint64)), ("ref_len", C.POINTER(C.c_uint32)),
                 ("kmers", C.POINTER(C.c_uint32))]
+
+
+class MFileJob(C.Structure):
+    _fields_ = [("file", C.c_void_p), ("idx_id", C.c_uint32), ("n_docs", C.c_uint32),
+                ("names", C.c_char_p), ("noffs", C.c_void_p)]
+
+
+class WriteStats(C.Structure):
+    _fields_ = [("format_s", C.c_double), ("deflate_s", C.c_double), ("write_s", C.c_double),
+                ("wall_s", C.c_double), ("text_bytes", C.c_uint64), ("file_bytes", C.c_uint64),
+                ("n_header_lines", C.c_uint64), ("n_hit_lines", C.c_uint64)]
 
 
 class IndexInfo(C.Structure):
@@ -109,6 +120,11 @@ PROTOTYPES = {
     "phy_text_free": (None, [C.c_void_p]),
     "phy_parse_match_text": (C.c_int, [C.c_char_p, C.c_uint64, C.POINTER(C.POINTER(MatchText))]),
     "phy_match_text_free": (None, [C.POINTER(MatchText)]),
+    "phy_mfile_open": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "phy_mfile_commit": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "phy_mfile_abort": (None, [C.c_void_p]),
+    "phy_write_match_blocks": (C.c_int, [C.POINTER(Results), C.POINTER(MFileJob), C.c_uint32, C.c_char_p, C.c_void_p,
+                                        C.c_void_p, C.c_int, C.c_int, C.POINTER(WriteStats)]),
     "phy_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "phy_nccl_init": (C.c_int, [_P, C.c_void_p, C.c_int, C.c_int]),
     "phy_timer_start": (C.c_int, [_P]),
@@ -116,6 +132,8 @@ PROTOTYPES = {
     "phy_sync": (C.c_int, [_P]),
     "phy_last_phase_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "phy_last_gather_bytes": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    "phy_last_gather_bytes_of": (C.c_int, [_P, C.c_int, C.POINTER(C.c_uint64)]),
+    "phy_ctx_budget": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "phy_ctx_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
     "phy_flush_l2": (C.c_int, [_P]),
     "phy_index_synth": (C.c_int, [_P, C.c_int, C.POINTER(SynthSpec)]),

@@ -46,22 +46,31 @@ def _die(msg, code=1):
 
 
 def _postprocess_stream(fin, fout, keep: int):
-    """Text filter with the exact semantics of postprocess_cobs.py:21-38."""
-    i, min_kmers = 0, 0
+    """Drop-in for `postprocess_cobs.py -n keep` (scripts/postprocess_cobs.py:21-38) on a text stream
+    (for real `cobs query` output; our own `cobs query --top-n` fuses this on the GPU).  Per query
+    block: names become "_" + text after the first "_", the first `keep` hit lines are kept plus
+    every later line whose count equals that of line number `keep` (cobs sorts by score, so those
+    are the ties).  keep <= 0 keeps the lines with count 0 only, as the script does."""
+    def flush(block):
+        if not block:
+            return
+        lines = ["_" + x.partition("_")[2] for x in block]
+        if 0 < keep < len(lines):
+            cut = int(lines[keep - 1].split("\t")[-1])
+            lines = lines[:keep] + [y for y in lines[keep:] if int(y.split("\t")[-1]) == cut]
+        elif keep <= 0:
+            lines = [y for y in lines if int(y.split("\t")[-1]) == 0]
+        fout.writelines(lines)
+
+    block = []
     for x in fin:
         if x[0] == "*":
-            i, min_kmers = 0, 0
+            flush(block)
+            block = []
             fout.write(x)
-            continue
-        y = "_" + x.partition("_")[2]
-        i += 1
-        if i < keep:
-            fout.write(y)
-        elif i == keep:
-            fout.write(y)
-            min_kmers = int(y.split("\t")[-1])
-        elif int(y.split("\t")[-1]) == min_kmers:
-            fout.write(y)
+        else:
+            block.append(x)
+    flush(block)
 
 
 def query_blocks(records, max_bases: int):
@@ -105,32 +114,8 @@ def cmd_cobs_query(a):
 
 
 # ------------------------------------------------------------------------------------ filter
-def parse_match_file(path):
-    """[(qname, [(ref, kmers)])] with the parsing rules of filter_queries.py:27-66."""
-    blocks = []
-    opener = gzip.open if str(path).endswith(".gz") else open
-    with opener(path, "rt") as f:
-        for x in f:
-            x = x.strip()
-            if not x:
-                continue
-            if x[0] == "*":
-                parts = x[1:].split("\t")
-                int(parts[1])
-                blocks.append((parts[0].split(" ")[0], []))
-            else:
-                if not blocks:
-                    raise ValueError(f"{path}: hit line before any query header")
-                tmp_name, kmers = x.split()
-                _rid, ref = tmp_name.split("_")       # exactly one underscore (filter_queries.py:64)
-                blocks[-1][1].append((ref, int(kmers)))
-    if not blocks:
-        raise ValueError(f"{path}: empty match file")
-    return blocks
-
-
 def parse_match_file_native(path):
-    """Same content as parse_match_file, produced by the library's C++ parser, as arrays:
+    """A match file parsed with the rules of filter_queries.py:27-66 by the library's C++ parser, as arrays:
     (qnames [str per block], first_hit uint64[n_blocks+1], ref_ids int64[n_hits], refs_sorted [str],
     kmers uint32[n_hits]); ref_ids index refs_sorted (byte order = Python str order for ASCII)."""
     import ctypes as C
@@ -253,22 +238,115 @@ def _atomic_write(path, data: bytes, gz: bool):
 
 
 def _spawn_match_db_workers(a):
-    """`match-db --gpus N`: one worker process per GPU (device = rank), NCCL merge on rank 0."""
+    """`match-db --gpus N`: one worker process per GPU (device = rank), NCCL merge on rank 0.
+    The parent supervises: the first worker that exits non-zero (bad index, PHY_ERR_NOMEM, a query
+    outside ACGT ...) takes the others down, which would otherwise block forever inside a
+    collective waiting for it; the job then exits non-zero (`set -euo pipefail` callers)."""
+    import shutil
     import subprocess
     import tempfile
-    id_file = os.path.join(tempfile.mkdtemp(prefix="phylign_nccl_"), "id")
+    import time
+    tmpdir = tempfile.mkdtemp(prefix="phylign_nccl_")
+    id_file = os.path.join(tmpdir, "id")
     argv = [x for x in sys.argv[1:]]
     procs = []
-    for r in range(a.gpus):
-        env = dict(os.environ, PHYLIGN_RANK=str(r), PHYLIGN_WORLD=str(a.gpus), PHYLIGN_NCCL_ID_FILE=id_file)
-        procs.append(subprocess.Popen([sys.executable, "-m", "phylign_b200.cli"] + argv, env=env))
-    rcs = [p.wait() for p in procs]
-    if any(rcs):
-        _die(f"match-db workers failed (exit codes {rcs})")
+    try:
+        for r in range(a.gpus):
+            env = dict(os.environ, PHYLIGN_RANK=str(r), PHYLIGN_WORLD=str(a.gpus), PHYLIGN_NCCL_ID_FILE=id_file)
+            procs.append(subprocess.Popen([sys.executable, "-m", "phylign_b200.cli"] + argv, env=env))
+        failed = None
+        while failed is None and any(p.poll() is None for p in procs):
+            for r, p in enumerate(procs):
+                if p.poll() not in (None, 0):
+                    failed = r
+                    break
+            else:
+                time.sleep(0.05)
+        if failed is None:
+            failed = next((r for r, p in enumerate(procs) if p.returncode != 0), None)
+        if failed is not None:
+            for p in procs:
+                if p.poll() is None:
+                    p.terminate()
+            deadline = time.time() + 10
+            for p in procs:
+                try:
+                    p.wait(timeout=max(0.1, deadline - time.time()))
+                except subprocess.TimeoutExpired:
+                    p.kill()
+                    p.wait()
+            _die(f"match-db worker {failed} failed (exit code {procs[failed].returncode}); "
+                 f"the other workers were stopped")
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+        shutil.rmtree(tmpdir, ignore_errors=True)
+
+
+def _wait_for_file(path, timeout_s: float):
+    """Contents of `path` once it exists; raises after timeout_s (rank 0 never published it)."""
+    import time
+    deadline = time.time() + timeout_s
+    while not os.path.exists(path):
+        if time.time() > deadline:
+            raise TimeoutError(f"NCCL id file {path} did not appear within {timeout_s:.0f} s "
+                               "(rank 0 failed before publishing it?)")
+        time.sleep(0.05)
+    with open(path, "rb") as f:
+        return f.read()
+
+
+class _Timing:
+    """Wall-clock seconds per phase of a match-db run (main thread), written as JSON on request."""
+
+    def __init__(self):
+        import time
+        self._now = time.perf_counter
+        self.t = {}
+        self._t0 = self._now()
+
+    def add(self, key, dt):
+        self.t[key] = self.t.get(key, 0.0) + dt
+
+    class _Span:
+        def __init__(self, owner, key):
+            self.o, self.k = owner, key
+
+        def __enter__(self):
+            self.t0 = self.o._now()
+
+        def __exit__(self, *exc):
+            self.o.add(self.k, self.o._now() - self.t0)
+
+    def span(self, key):
+        return _Timing._Span(self, key)
+
+    def total(self):
+        return self._now() - self._t0
+
+
+def _write_benchmark_log(path, command, wall_s, extra_cols):
+    """One log in the format family of scripts/benchmark.py:33-46,64-67: a `# Benchmarking command:`
+    line, a tab-separated header and one value line.  The 8 reference columns come first (those
+    /usr/bin/time would measure per process are n/a for a batch that shared one resident job);
+    the match-stage columns follow."""
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    head = ["real(s)", "sys(s)", "user(s)", "percent_CPU", "max_RAM(kb)", "FS_inputs", "FS_outputs",
+            "elapsed_time_alt(s)"] + [k for k, _ in extra_cols]
+    vals = [f"{wall_s:.3f}", "NA", "NA", "NA", "NA", "NA", "NA", f"{wall_s:.3f}"] + [str(v) for _, v in extra_cols]
+    with open(path, "w") as f:
+        f.write(f"# Benchmarking command: {command}\n" + "\t".join(head) + "\n" + "\t".join(vals) + "\n")
 
 
 def cmd_match_db(a):
+    import json
+    import time
+    from concurrent.futures import ThreadPoolExecutor as _TPE
     from .matcher import Matcher, nccl_unique_id
+    from .match_files import MatchFileSet
+    from .cobs_text import _cat
+    tm = _Timing()
     rank = int(os.environ.get("PHYLIGN_RANK", -1))
     world = int(os.environ.get("PHYLIGN_WORLD", 1))
     if a.gpus > 1 and rank < 0:
@@ -278,7 +356,8 @@ def cmd_match_db(a):
         _die("--gpus and --shard are alternatives")
     with open(a.batches) as f:
         batches = sorted(filter(len, map(str.strip, f)))      # Snakefile:32-34
-    records = fasta.read_cobs_records(a.q)
+    with tm.span("read_queries_s"):
+        records = fasta.read_cobs_records(a.q)
     qfile = a.qfile or os.path.splitext(os.path.basename(a.q))[0]
     os.makedirs(a.match_dir, exist_ok=True)
     sizes = {}
@@ -292,8 +371,20 @@ def cmd_match_db(a):
     from .cobs_index import IndexStream
 
     def path_of(b):
+        """Where batch b is read from: the decompressed copy of the reference's `decompress_cobs` rule
+        (Snakefile:364-387, {decompression_dir}/{batch}.cobs_classic) when there is one, else the .xz."""
+        if a.decompression_dir:
+            p = os.path.join(a.decompression_dir, f"{b}.cobs_classic")
+            if os.path.exists(p):
+                return p
         p = os.path.join(a.cobs_dir, f"{b}.cobs_classic.xz")
         return p if os.path.exists(p) else p[:-3]
+
+    def keep_path_of(b):
+        """Decompressed copy to leave behind while streaming the .xz (config.yaml keep_cobs_indexes)."""
+        if a.keep_cobs_indexes and a.decompression_dir and path_of(b).endswith(".xz"):
+            return os.path.join(a.decompression_dir, f"{b}.cobs_classic")
+        return None
 
     merged_inputs, todo = [], []
     for b in batches:
@@ -302,102 +393,211 @@ def cmd_match_db(a):
             merged_inputs.append(out)
         else:
             todo.append(b)
-    shapes = {}
-    for b in todo:      # shapes come from the index headers (the first bytes of each xz stream)
-        if not os.path.exists(path_of(b)):
-            _die(f"index of batch {b} not found under {a.cobs_dir}")
-        st = IndexStream(path_of(b))
-        h = st.header
-        st.abort()
-        shapes[b] = sharding.Batch(b, h.n_docs, h.signature_size)
-        if b in sizes and sizes[b] != h.header_size + h.body_size:
-            _die(f"{b}: decompressed size {h.header_size + h.body_size} != table {sizes[b]}")
+    shapes, headers_of = {}, {}
+    with tm.span("plan_s"):
+        for b in todo:      # shapes come from the index headers (the first bytes of each stream)
+            if not os.path.exists(path_of(b)):
+                _die(f"index of batch {b} not found under {a.cobs_dir}")
+            st = IndexStream(path_of(b))
+            h = st.header
+            st.abort()
+            headers_of[b] = h
+            shapes[b] = sharding.Batch(b, h.n_docs, h.signature_size)
+            if b in sizes and sizes[b] != h.header_size + h.body_size:
+                _die(f"{b}: decompressed size {h.header_size + h.body_size} != table {sizes[b]}")
     n_shards, shard = 1, 0
     if a.shard:
         shard, n_shards = (int(x) for x in a.shard.split("/"))
     if nccl:
         shard, n_shards = rank, world
-    budget = a.round_bytes or (int(a.hbm_budget * 0.9) if a.hbm_budget else 160 * 10 ** 9)
-    plan = sharding.assign([shapes[b] for b in todo], n_shards, budget) if todo else sharding.Plan(n_shards)
-    # 04_filter is merged from the device results of every round (no re-parsing of what was just
-    # written); only match files that already existed (--resume) are parsed
-    want_filter = bool(a.filter_out) and (n_shards == 1 or nccl)
-    if a.filter_out and not want_filter:
-        _die("--filter-out needs all batches: use --gpus N, or run `filter` over the match files of all shards")
-    collect = want_filter and (not nccl or rank == 0)     # who assembles 04_filter
-    queries, qid = _load_filter_queries(a.q) if collect else ({}, {})
-    brank = sharding.global_batch_ranks(batches)
-    rec2qid = np.array([qid[h.split(" ")[0]] for h, _ in records], dtype=np.int64) if collect else None
-    pieces, refs_by_rank = [], {}
-    if collect and merged_inputs:
-        pieces, refs_by_rank = _parsed_pieces(merged_inputs, qid, brank, open(os.devnull, "w"))
+    total_bases = sum(len(s) for _, s in records)
     with Matcher(rank if nccl else a.device, a.hbm_budget) as m:
+        # HBM left for indexes = the context's budget minus the working set of one query block
+        # (hashes 8 B per base, sequence 1 B, unit tables, result/merge buffers)
+        block_bases = min(total_bases, a.query_block_bases)
+        working = 10 * block_bases + 24 * len(records) + (2 << 30)
+        free_for_indexes = max(0, m.budget_bytes() - working)
+        budget = min(a.round_bytes, free_for_indexes) if a.round_bytes else int(free_for_indexes * 0.95)
+        try:
+            plan = sharding.assign([shapes[b] for b in todo], n_shards, budget) if todo else sharding.Plan(n_shards)
+        except ValueError as e:
+            _die(f"{e} (index budget {budget} B = HBM budget {m.budget_bytes()} B minus {working} B for a query "
+                 f"block of {block_bases} bases: lower --query-block-bases or raise --hbm-budget)")
+        overlap = a.overlap_rounds and len(plan.rounds) > 1
+        if overlap:                                           # two rounds resident at once: halve the round size
+            plan = sharding.assign([shapes[b] for b in todo], n_shards, budget // 2)
+        # 04_filter is merged from the device results of every round (no re-parsing of what was just
+        # written); only match files that already existed (--resume) are parsed
+        want_filter = bool(a.filter_out) and (n_shards == 1 or nccl)
+        if a.filter_out and not want_filter:
+            _die("--filter-out needs all batches: use --gpus N, or run `filter` over the match files of all shards")
+        collect = want_filter and (not nccl or rank == 0)     # who assembles 04_filter
+        queries, qid = _load_filter_queries(a.q) if collect else ({}, {})
+        brank = sharding.global_batch_ranks(batches)
+        rec2qid = np.array([qid[h.split(" ")[0]] for h, _ in records], dtype=np.int64) if collect else None
+        identity = collect and len(queries) == len(records) and bool((rec2qid == np.arange(len(records))).all())
+        pieces, refs_by_rank = [], {}
+        if collect and merged_inputs:
+            with tm.span("parse_existing_s"):
+                pieces, refs_by_rank = _parsed_pieces(merged_inputs, qid, brank, open(os.devnull, "w"))
         if nccl:                                              # rank 0 publishes the NCCL id through a file
             id_file = os.environ["PHYLIGN_NCCL_ID_FILE"]
             if rank == 0:
                 with open(id_file + ".tmp", "wb") as f:
                     f.write(nccl_unique_id())
                 os.replace(id_file + ".tmp", id_file)
-            import time
-            for _ in range(6000):
-                if os.path.exists(id_file):
-                    break
-                time.sleep(0.05)
-            m.nccl_init(open(id_file, "rb").read(), rank, world)
-        for rnd in plan.rounds:                               # resident round: load, match, write, evict
-            mine = sorted(x.name for x in rnd[shard])
-            if not mine and not (nccl and want_filter):
-                continue                                      # (under NCCL every rank joins every merge)
-            loaded = m.load_indexes([path_of(b) for b in mine], mine, workers=a.load_workers) if mine else []
-            m.set_ranks(batches)
-            texts = {idx: [] for idx in loaded}               # per index: one text piece per query block
-            n_hit_queries = {idx: 0 for idx in loaded}
-            for q0, block in query_blocks(records, a.query_block_bases):
-                m.set_queries(block)
-                m.match_run(a.t, top_n=a.n, floor_mode=a.floor, merge_top_n=a.n if want_filter else 0)
-                res = m.fetch()
-                if loaded:
-                    format_cobs_text_fast(block, res, m.indexes[loaded[0]], strip_prefix=True)   # warm the header cache
-                with ThreadPoolExecutor(max_workers=max(1, a.load_workers)) as ex:   # C++ formatter releases the GIL
-                    for idx, text in zip(loaded, ex.map(
-                            lambda i: format_cobs_text_fast(block, res, m.indexes[i], strip_prefix=True), loaded)):
-                        texts[idx].append(text)
-                        n_hit_queries[idx] += len(res.units_of(idx))
-                if collect:                                   # this block's top-N + ties per query and round
-                    moffs, mc = m.merged()
-                    q_of = q0 + np.repeat(np.arange(len(block), dtype=np.int64), np.diff(moffs.astype(np.int64)))
-                    pieces.append((rec2qid[q_of], np.array(mc)))
+            m.nccl_init(_wait_for_file(id_file, float(os.environ.get("PHYLIGN_NCCL_ID_TIMEOUT", 300))), rank, world)
+        blocks = list(query_blocks(records, a.query_block_bases))
+        block_hdrs = [_cat([h for h, _ in blk]) for _, blk in blocks]
+        wstats, gpu_phase_ms, gathered_total, n_writer_blocks = [], np.zeros(3), 0, 0
+        direct_merged = None                                   # (owner ptr) when one device merge is already final
+        bg = _TPE(max_workers=1)                               # the writer thread (format + gzip + append)
+        loader = _TPE(max_workers=1)                           # next round's indexes (--overlap-rounds)
+        rounds = [sorted(x.name for x in rnd[shard]) for rnd in plan.rounds]
 
-            def write_one(idx):       # gzip (zlib) releases the GIL: one thread per file
-                ix = m.indexes[idx]
-                _atomic_write(os.path.join(a.match_dir, f"{ix.batch}____{qfile}.gz"), b"".join(texts[idx]), gz=True)
-                return idx
+        def load_round(names):
+            t0 = time.perf_counter()
+            ids = m.load_indexes([path_of(b) for b in names], names, workers=a.load_workers,
+                                 keep_paths=[keep_path_of(b) for b in names], active=False) if names else []
+            return ids, time.perf_counter() - t0
 
-            with ThreadPoolExecutor(max_workers=max(1, a.load_workers)) as ex:
-                for idx in ex.map(write_one, loaded):
+        pending_load = None
+        try:
+            for ri, mine in enumerate(rounds):                 # resident round: load, match, write, evict
+                if pending_load is None:
+                    pending_load = loader.submit(load_round, mine)
+                t0 = time.perf_counter()
+                loaded, load_s = pending_load.result()
+                tm.add("index_load_s", load_s)
+                tm.add("index_load_wait_s", time.perf_counter() - t0)
+                pending_load = None
+                if overlap and ri + 1 < len(rounds):           # decode + push round r+1 while r is matched
+                    pending_load = loader.submit(load_round, rounds[ri + 1])
+                if not mine and not (nccl and want_filter):
+                    continue                                   # (under NCCL every rank joins every merge)
+                m.set_ranks(batches)
+                m.set_active_only(loaded)
+                fs = MatchFileSet({idx: os.path.join(a.match_dir, f"{m.indexes[idx].batch}____{qfile}.gz")
+                                   for idx in loaded}, m.indexes, gzip_level=1, threads=a.write_threads)
+                n_hit_queries = {idx: 0 for idx in loaded}
+                round_t0 = time.perf_counter()
+                round_gpu_ms, round_bytes_by_idx = 0.0, {idx: 0 for idx in loaded}
+                fut = None
+                try:
+                    for bi, (q0, block) in enumerate(blocks):
+                        if len(blocks) > 1 or ri == 0:          # one block: queries stay resident across rounds
+                            with tm.span("set_queries_s"):
+                                m.set_queries(block)
+                        with tm.span("gpu_match_s"):
+                            m.match_run(a.t, top_n=a.n, floor_mode=a.floor, merge_top_n=a.n if want_filter else 0)
+                        ph = m.phase_ms()
+                        gpu_phase_ms += ph[:3]
+                        round_gpu_ms += float(sum(ph[:3]))
+                        gathered_total += m.gathered_bytes()
+                        for idx in loaded:
+                            round_bytes_by_idx[idx] += m.gathered_bytes_of(idx)
+                        with tm.span("fetch_results_s"):
+                            res = m.fetch()
+                        for idx in loaded:
+                            n_hit_queries[idx] += len(res.units_of(idx))
+                        if fut is not None:                     # at most one block in flight behind the GPU
+                            with tm.span("writer_wait_s"):
+                                fut.result()
+                        hcat, hoffs = block_hdrs[bi]
+                        fut = bg.submit(lambda r=res, hc=hcat, ho=hoffs: fs.write_block(hc, ho, r._owner.ptr))
+                        n_writer_blocks += 1
+                        if collect:                             # this block's top-N + ties per query and round
+                            with tm.span("fetch_merged_s"):
+                                moffs, mc = m.merged()
+                            if identity and len(rounds) == 1 and len(blocks) == 1 and not pieces:
+                                direct_merged = m._merged_owner   # already the global answer: no host re-merge
+                            else:
+                                q_of = q0 + np.repeat(np.arange(len(block), dtype=np.int64),
+                                                      np.diff(moffs.astype(np.int64)))
+                                pieces.append((rec2qid[q_of], np.array(mc)))
+                        elif nccl and want_filter:
+                            m.merged()                          # non-holders still take part in the fetch
+                    if fut is not None:
+                        with tm.span("writer_wait_s"):
+                            fut.result()
+                    with tm.span("commit_files_s"):
+                        fs.commit()
+                except BaseException:
+                    if fut is not None:
+                        try:
+                            fut.result()
+                        except Exception:
+                            pass
+                    fs.abort()
+                    raise
+                wstats.append(fs.stats_dict())
+                round_wall = time.perf_counter() - round_t0
+                kmers = sum(max(len(s) - 30, 0) for _, s in records)
+                round_alg = sum((m.indexes[i].header.n_docs + 7) // 8 for i in loaded) or 1
+                for idx in loaded:
                     ix = m.indexes[idx]
                     print(f"[match-db] {ix.batch}: {n_hit_queries[idx]} queries with hits", file=sys.stderr)
                     refs_by_rank[ix.batch_rank] = [_ref_of(n) for n in ix.doc_names]
-            for idx in loaded:
-                m.evict(idx)
+                    if a.benchmark_dir:                         # logs/benchmarks/run_cobs/{batch}____{qfile}.txt
+                        rb = (ix.header.n_docs + 7) // 8
+                        share = rb / round_alg                  # of the round (one fused launch per row class)
+                        wall = round_wall * share
+                        _write_benchmark_log(
+                            os.path.join(a.benchmark_dir, f"{ix.batch}____{qfile}.txt"),
+                            f"phylign_b200 match-db (resident round {ri}, {len(loaded)} batches on GPU "
+                            f"{m.device}; per-batch share by row bytes)", wall,
+                            [("batch", ix.batch), ("qfile", qfile), ("gpu_ms", f"{round_gpu_ms * share:.3f}"),
+                             ("bases/s", f"{total_bases / max(wall, 1e-9):.4g}"),
+                             ("kmer_docs/s", f"{kmers * ix.header.n_docs / max(wall, 1e-9):.4g}"),
+                             ("GB/s_gathered", f"{round_bytes_by_idx[idx] / max(round_gpu_ms * share, 1e-9) / 1e6:.1f}"),
+                             ("rows_read/all", f"{round_bytes_by_idx[idx] / max(1, kmers * rb):.4f}"),
+                             ("match_file_bytes", fs.file_bytes.get(idx, 0))])
+                with tm.span("evict_s"):
+                    for idx in loaded:
+                        m.evict(idx)
+        finally:
+            if pending_load is not None:
+                try:
+                    pending_load.result()
+                except Exception:
+                    pass
+            bg.shutdown(wait=True)
+            loader.shutdown(wait=True)
         if collect and nccl:                                  # accessions of the batches other ranks hold
             for b in todo:
                 if brank[b] not in refs_by_rank:
-                    st = IndexStream(path_of(b))
-                    refs_by_rank[brank[b]] = [_ref_of(n) for n in st.header.doc_names]
-                    st.abort()
+                    refs_by_rank[brank[b]] = [_ref_of(n) for n in headers_of[b].doc_names]
         if collect:
-            fa = _final_merge(m, queries, pieces, refs_by_rank, a.n)
-            os.makedirs(os.path.dirname(os.path.abspath(a.filter_out)), exist_ok=True)
-            _atomic_write(a.filter_out, fa.encode(), gz=False)
+            with tm.span("final_merge_s"):
+                if direct_merged is not None:
+                    fa = format_filter_fasta_fast(list(queries.items()), direct_merged.ptr, refs_by_rank)
+                else:
+                    fa = _final_merge(m, queries, pieces, refs_by_rank, a.n).encode()
+            with tm.span("write_filter_s"):
+                os.makedirs(os.path.dirname(os.path.abspath(a.filter_out)), exist_ok=True)
+                _atomic_write(a.filter_out, fa, gz=False)
             if a.bucket_dir:      # per-batch "reference -> queries to align" tables for stage 05
                 from .cobs_text import candidate_buckets, format_bucket_tsv
-                moffs, mc = m.merged()
-                buckets = candidate_buckets(list(queries), moffs, mc, refs_by_rank)
-                os.makedirs(a.bucket_dir, exist_ok=True)
-                for b in batches:
-                    _atomic_write(os.path.join(a.bucket_dir, f"{b}____{qfile}.candidates.tsv"),
-                                  format_bucket_tsv(buckets.get(brank[b], [])).encode(), gz=False)
+                with tm.span("buckets_s"):
+                    moffs, mc = m.merged()
+                    buckets = candidate_buckets(list(queries), moffs, mc, refs_by_rank)
+                    os.makedirs(a.bucket_dir, exist_ok=True)
+                    for b in batches:
+                        _atomic_write(os.path.join(a.bucket_dir, f"{b}____{qfile}.candidates.tsv"),
+                                      format_bucket_tsv(buckets.get(brank[b], [])).encode(), gz=False)
+        if a.timing_json and (not nccl or rank == 0):
+            w = {k: sum(d[k] for d in wstats) for k in (wstats[0] if wstats else {}) if k != "threads"}
+            out = {"total_s": tm.total(), "phases_s": {k: round(v, 4) for k, v in tm.t.items()},
+                   "writer": dict(w, threads=wstats[0]["threads"] if wstats else 0, blocks=n_writer_blocks),
+                   "gpu_phase_ms_hash_gather_merge": [round(float(x), 3) for x in gpu_phase_ms],
+                   "gathered_bytes": int(gathered_total), "rounds": len(rounds), "query_blocks": len(blocks),
+                   "overlap_rounds": bool(overlap), "n_queries": len(records), "bases": int(total_bases),
+                   "n_batches": len(todo), "rank": max(rank, 0), "world": world,
+                   "direct_device_merge": direct_merged is not None}
+            tmp = a.timing_json + f".tmp.{os.getpid()}"
+            with open(tmp, "w") as f:
+                json.dump(out, f)
+            os.replace(tmp, a.timing_json)
 
 
 # ------------------------------------------------------------------------------------ argparse
@@ -485,6 +685,20 @@ def build_parser():
                    help="HBM bytes of indexes resident at once (default 90%% of --hbm-budget, else 160e9); "
                         "batches beyond it are streamed through in further rounds")
     d.add_argument("--device", type=int, default=0)
+    d.add_argument("--write-threads", type=int, default=0,
+                   help="host threads that format + gzip the match files (default: all cores)")
+    d.add_argument("--decompression-dir", default=None,
+                   help="{decompression_dir} of the reference (config.yaml): a {batch}.cobs_classic found there is "
+                        "loaded instead of the .xz (no LZMA decode)")
+    d.add_argument("--keep-cobs-indexes", action="store_true",
+                   help="leave the decompressed {batch}.cobs_classic in --decompression-dir while streaming the .xz "
+                        "(config.yaml keep_cobs_indexes; same bytes as rule decompress_cobs writes)")
+    d.add_argument("--no-overlap-rounds", dest="overlap_rounds", action="store_false",
+                   help="when the batches need several resident rounds: do not load round r+1 while round r is "
+                        "matched (default: overlap, each round then uses half of the index budget)")
+    d.add_argument("--benchmark-dir", default=None,
+                   help="write logs/benchmarks/run_cobs-style {batch}____{qfile}.txt files (scripts/benchmark.py format)")
+    d.add_argument("--timing-json", default=None, help="write the wall-clock breakdown of the run here")
     d.set_defaults(fn=cmd_match_db)
     return ap
 

@@ -71,18 +71,20 @@ def read_header(f) -> ClassicHeader:
         raise IndexFormatError(f"unsupported classic index version {version}")
     names = []
     size = 5 + 13 + 29
-    buf = b""
+    buf, pos = b"", 0               # names are cut out of `buf` at a moving offset (no re-copying)
     while len(names) < n_docs:
-        nl = buf.find(b"\n")
+        nl = buf.find(b"\n", pos)
         if nl < 0:
             more = f.read(65536)   # may run into the body: the excess is carried over
             if not more:
                 raise IndexFormatError("truncated document name table")
-            buf += more
+            buf = buf[pos:] + more
+            pos = 0
             continue
-        names.append(buf[:nl].decode())
-        size += nl + 1
-        buf = buf[nl + 1:]
+        names.append(buf[pos:nl].decode())
+        size += nl + 1 - pos
+        pos = nl + 1
+    buf = buf[pos:]
     # `buf` may already hold bytes past the name table: end magic (+ body)
     need = 13 - len(buf)
     if need > 0:

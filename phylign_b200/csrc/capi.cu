@@ -121,7 +121,7 @@ extern "C" void phy_ctx_destroy(phy_ctx* ctx) {
                     ctx->d_qcount.p, ctx->d_scores.p, ctx->d_items.p, ctx->d_slotq.p, ctx->d_ckey.p, ctx->d_qoffs_c.p,
                     ctx->d_foffs.p, ctx->d_scan_tmp.p, ctx->d_cval.p, ctx->d_qcursor.p, ctx->d_nfinal.p,
                     ctx->d_final.p, ctx->d_flush.p, ctx->d_foffs_all.p, ctx->d_rank_base.p,
-                    ctx->d_recv.p, ctx->d_units_sorted.p, ctx->d_unit_flag.p, ctx->d_unit_id.p, ctx->d_unit_pos.p, ctx->d_ioffs.p};
+                    ctx->d_idx_bytes.p, ctx->d_recv.p, ctx->d_units_sorted.p, ctx->d_unit_flag.p, ctx->d_unit_id.p, ctx->d_unit_pos.p, ctx->d_ioffs.p};
     for (void* b : bufs) if (b) cudaFree(b);
     for (int i = 0; i < 2; i++) {
         if (ctx->pin[i]) cudaFreeHost(ctx->pin[i]);
@@ -776,6 +776,17 @@ extern "C" int phy_last_phase_ms(phy_ctx* ctx, float out[4]) {
 extern "C" int phy_last_gather_bytes(phy_ctx* ctx, uint64_t* bytes) {
     if (!ctx || !bytes) return PHY_ERR_ARG;
     *bytes = ctx->gathered_bytes;
+    return PHY_OK;
+}
+extern "C" int phy_last_gather_bytes_of(phy_ctx* ctx, int idx_id, uint64_t* bytes) {
+    if (!ctx || !bytes || idx_id < 0) return PHY_ERR_ARG;
+    *bytes = (size_t)idx_id < ctx->h_idx_bytes.size() ? ctx->h_idx_bytes[idx_id] : 0;
+    return PHY_OK;
+}
+extern "C" int phy_ctx_budget(phy_ctx* ctx, uint64_t* budget, uint64_t* used) {
+    if (!ctx) return PHY_ERR_ARG;
+    if (budget) *budget = ctx->budget;
+    if (used) *used = ctx->used;
     return PHY_OK;
 }
 extern "C" int phy_ctx_set_option(phy_ctx* ctx, const char* name, int64_t value) {

@@ -197,6 +197,7 @@ struct GatherArgs {
     uint32_t* unit_id;    // [index slot][query] position in units[]
     uint32_t nq;
     uint32_t prune;       // threshold pruning on (ring kernel)
+    unsigned long long* idx_bytes;  // [index slot] index-row bytes really gathered (ring kernel)
 };
 
 // Threshold (cobs counts_to_result), top-N + ties (postprocess_cobs.py:21-38) and emission of
@@ -734,7 +735,7 @@ gather_count_ring_kernel(const GatherArgs a) {
         const uint32_t done = ring_accumulate<LPR, P, NB>(pl, ring, colbase, (uint32_t)col * 16u < stride, stride,
                                                           sig, magic, hq, nrows, nmax, lane, prune_T, gm);
         if (live && col == 0)  // bytes of index rows this unit really gathered (pruning makes it < K rows)
-            atomicAdd(&a.counters[5], (unsigned long long)done * ((n_docs + 7u) >> 3));
+            atomicAdd(&a.idx_bytes[idx_id], (unsigned long long)done * ((n_docs + 7u) >> 3));
         if (live) select_and_emit<LPR, P>(pl, a, q, idx_id, n_docs, nrows, lane, gm);
         __syncwarp();
     }
@@ -1184,7 +1185,8 @@ int phy_launch_gather(phy_ctx* ctx, const phy_match_params* p) {
         PHY_TRY(phy_ensure(ctx, ctx->d_units, units_cap));
         PHY_TRY(phy_ensure(ctx, ctx->d_hits, hits_cap));
         PHY_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, 2 * sizeof(unsigned long long), ctx->stream));
-        PHY_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p + 5, 0, sizeof(unsigned long long), ctx->stream));
+        PHY_TRY(phy_ensure(ctx, ctx->d_idx_bytes, ctx->idx.size() + 1));
+        PHY_CUDA(ctx, cudaMemsetAsync(ctx->d_idx_bytes.p, 0, (ctx->idx.size() + 1) * sizeof(unsigned long long), ctx->stream));
         PHY_CUDA(ctx, cudaMemsetAsync(ctx->d_qcount.p, 0, (ctx->nq + 1) * sizeof(uint32_t), ctx->stream));
         GatherArgs a;
         a.indexes = ctx->d_indexes.p;
@@ -1196,6 +1198,7 @@ int phy_launch_gather(phy_ctx* ctx, const phy_match_params* p) {
         a.units = ctx->d_units.p; a.units_cap = ctx->d_units.cap;
         a.hits = ctx->d_hits.p; a.hits_cap = ctx->d_hits.cap;
         a.counters = ctx->d_counters.p; a.qcount = ctx->d_qcount.p;
+        a.idx_bytes = ctx->d_idx_bytes.p;
         // dense (index slot, query) table so the unit list can be put in (index, query) order on
         // the device (deterministic output, no host sort); skipped when it would be huge
         const uint64_t cells = (uint64_t)ctx->idx.size() * ctx->nq;
@@ -1287,9 +1290,13 @@ int phy_launch_gather(phy_ctx* ctx, const phy_match_params* p) {
             }
         }
         unsigned long long cnt[6];
+        ctx->h_idx_bytes.assign(ctx->idx.size() + 1, 0);
         PHY_CUDA(ctx, cudaMemcpyAsync(cnt, ctx->d_counters.p, sizeof cnt, cudaMemcpyDeviceToHost, ctx->stream));
+        PHY_CUDA(ctx, cudaMemcpyAsync(ctx->h_idx_bytes.data(), ctx->d_idx_bytes.p,
+                                      ctx->idx.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
         PHY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        ctx->gathered_bytes = cnt[5];
+        ctx->gathered_bytes = 0;
+        for (unsigned long long b : ctx->h_idx_bytes) ctx->gathered_bytes += b;
         if (cnt[0] <= ctx->d_hits.cap && cnt[1] <= ctx->d_units.cap) {
             ctx->n_hits = cnt[0];
             ctx->n_units = cnt[1];

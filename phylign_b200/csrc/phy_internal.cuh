@@ -92,6 +92,8 @@ struct phy_ctx {
     DevBuf<uint64_t> d_unit_pos;
     bool units_ordered = false;
     DevBuf<phy_hit> d_hits;
+    DevBuf<unsigned long long> d_idx_bytes; // [index slot] row bytes gathered by the last match
+    std::vector<unsigned long long> h_idx_bytes;
     DevBuf<unsigned long long> d_counters;  // [0] n_hits [1] n_units [2] error info
     DevBuf<uint32_t> d_qcount;              // kept hits per query (merge sizing)
     uint64_t n_units = 0, n_hits = 0;

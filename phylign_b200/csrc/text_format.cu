@@ -12,12 +12,6 @@
 #include "phy_internal.cuh"
 
 namespace {
-inline void put_u32(std::string& s, uint32_t v) {
-    char buf[12];
-    int n = 0;
-    do { buf[n++] = (char)('0' + v % 10); v /= 10; } while (v);
-    while (n) s.push_back(buf[--n]);
-}
 char* to_c(const std::string& s, uint64_t* len) {
     char* p = (char*)malloc(s.size() + 1);
     if (!p) return nullptr;
@@ -28,50 +22,95 @@ char* to_c(const std::string& s, uint64_t* len) {
 }
 }  // namespace
 
+// ---- formatting core shared by phy_format_cobs_text and the match-file writer --------------------
+// Appends the cobs text of queries [q0,q1) for one index to `out`.  Capacity is computed up
+// front from the header bytes and the kept-hit counts, so the inner loops are plain memcpy.
+int phy_format_cobs_range(const phy_results* r, uint32_t idx_id, uint32_t q0, uint32_t q1, const char* headers,
+                          const uint64_t* hoffs, const uint8_t* skip, const char* names, const uint64_t* noffs,
+                          uint32_t n_docs, int strip_prefix, std::vector<char>& out, uint64_t* n_header_lines,
+                          uint64_t* n_hit_lines) {
+    const phy_unit* ulo = std::lower_bound(r->units, r->units + r->n_units, idx_id,
+                                           [](const phy_unit& u, uint32_t i) { return u.index < i; });
+    const phy_unit* uhi = std::upper_bound(ulo, (const phy_unit*)(r->units + r->n_units), idx_id,
+                                           [](uint32_t i, const phy_unit& u) { return i < u.index; });
+    const phy_unit* u = std::lower_bound(ulo, uhi, q0, [](const phy_unit& x, uint32_t q) { return x.query < q; });
+    const phy_unit* uend = std::lower_bound(u, uhi, q1, [](const phy_unit& x, uint32_t q) { return x.query < q; });
+    uint64_t max_name = 0;
+    if (u < uend)
+        for (uint32_t d = 0; d < n_docs; d++) max_name = std::max<uint64_t>(max_name, noffs[d + 1] - noffs[d]);
+    uint64_t kept = 0;
+    for (const phy_unit* x = u; x < uend; x++) kept += x->n_kept;
+    const size_t base = out.size();
+    out.resize(base + (hoffs[q1] - hoffs[q0]) + (uint64_t)(q1 - q0) * 14 + kept * (max_name + 13) + 16);
+    char* w = out.data() + base;
+    auto put = [&](uint32_t v) {
+        char buf[12];
+        int n = 0;
+        do { buf[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+        while (n) *w++ = buf[--n];
+    };
+    uint64_t nh = 0, nl = 0;
+    for (uint32_t q = q0; q < q1; q++) {
+        const bool mine = u < uend && u->query == q;
+        const phy_unit* cur = u;
+        if (mine) u++;
+        if (skip && skip[q]) continue;   // record without sequence: cobs never runs it
+        *w++ = '*';
+        const size_t hl = hoffs[q + 1] - hoffs[q];
+        memcpy(w, headers + hoffs[q], hl);
+        w += hl;
+        *w++ = '\t';
+        nh++;
+        if (!mine) {
+            *w++ = '0';
+            *w++ = '\n';
+            continue;
+        }
+        put(cur->n_pass);
+        *w++ = '\n';
+        const phy_hit* h = r->hits + cur->offset;
+        for (uint32_t i = 0; i < cur->n_kept; i++) {
+            if (h[i].doc >= n_docs) return PHY_ERR_ARG;
+            const char* nm = names + noffs[h[i].doc];
+            size_t len = noffs[h[i].doc + 1] - noffs[h[i].doc];
+            if (strip_prefix) {  // "_" + text after the first underscore (postprocess_cobs.py:16-18)
+                const char* us = (const char*)memchr(nm, '_', len);
+                *w++ = '_';
+                if (us) {
+                    const size_t rest = len - (size_t)(us + 1 - nm);
+                    memcpy(w, us + 1, rest);
+                    w += rest;
+                }
+            } else {
+                memcpy(w, nm, len);
+                w += len;
+            }
+            *w++ = '\t';
+            put(h[i].score);
+            *w++ = '\n';
+        }
+        nl += cur->n_kept;
+    }
+    out.resize((size_t)(w - out.data()));
+    if (n_header_lines) *n_header_lines += nh;
+    if (n_hit_lines) *n_hit_lines += nl;
+    return PHY_OK;
+}
+
 extern "C" int phy_format_cobs_text(const phy_results* r, uint32_t idx_id, const char* headers, const uint64_t* hoffs,
                                     const uint8_t* skip, const char* names, const uint64_t* noffs, uint32_t n_docs,
                                     int strip_prefix, char** out, uint64_t* out_len) {
     if (!r || !headers || !hoffs || !names || !noffs || !out || !out_len) return PHY_ERR_ARG;
-    const phy_unit* lo = std::lower_bound(r->units, r->units + r->n_units, idx_id,
-                                          [](const phy_unit& u, uint32_t i) { return u.index < i; });
-    const phy_unit* hi = lo;
-    while (hi < r->units + r->n_units && hi->index == idx_id) hi++;
-    std::string s;
-    uint64_t est = 0;
-    for (const phy_unit* u = lo; u < hi; u++) est += (uint64_t)u->n_kept * 24;
-    s.reserve(est + (hoffs[r->n_queries] - hoffs[0]) + (uint64_t)r->n_queries * 8 + 64);
-    const phy_unit* u = lo;
-    for (uint32_t q = 0; q < r->n_queries; q++) {
-        while (u < hi && u->query < q) u++;
-        if (skip && skip[q]) continue;   // record without sequence: cobs never runs it
-        s.push_back('*');
-        s.append(headers + hoffs[q], hoffs[q + 1] - hoffs[q]);
-        s.push_back('\t');
-        if (u < hi && u->query == q) {
-            put_u32(s, u->n_pass);
-            s.push_back('\n');
-            const phy_hit* h = r->hits + u->offset;
-            for (uint32_t i = 0; i < u->n_kept; i++) {
-                if (h[i].doc >= n_docs) return PHY_ERR_ARG;
-                const char* nm = names + noffs[h[i].doc];
-                size_t len = noffs[h[i].doc + 1] - noffs[h[i].doc];
-                if (strip_prefix) {  // "_" + text after the first underscore
-                    const char* us = (const char*)memchr(nm, '_', len);
-                    s.push_back('_');
-                    if (us) s.append(us + 1, len - (size_t)(us + 1 - nm));
-                } else {
-                    s.append(nm, len);
-                }
-                s.push_back('\t');
-                put_u32(s, h[i].score);
-                s.push_back('\n');
-            }
-        } else {
-            s.append("0\n");
-        }
-    }
-    *out = to_c(s, out_len);
-    return *out ? PHY_OK : PHY_ERR_NOMEM;
+    std::vector<char> buf;
+    PHY_TRY(phy_format_cobs_range(r, idx_id, 0, r->n_queries, headers, hoffs, skip, names, noffs, n_docs, strip_prefix,
+                                  buf, nullptr, nullptr));
+    char* p = (char*)malloc(buf.size() + 1);
+    if (!p) return PHY_ERR_NOMEM;
+    memcpy(p, buf.data(), buf.size());
+    p[buf.size()] = 0;
+    *out = p;
+    *out_len = buf.size();
+    return PHY_OK;
 }
 
 extern "C" int phy_format_filter_fasta(const phy_merged* m, const char* qnames, const uint64_t* qnoffs,

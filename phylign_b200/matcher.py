@@ -47,10 +47,14 @@ class _Owned:
 
 
 def _view(ptr, n, dtype, owner):
-    """Zero-copy numpy view of n records at a ctypes pointer (pinned, owned by `owner`)."""
+    """Zero-copy numpy view of n records at a ctypes pointer (pinned, owned by `owner`).
+    The array (and every slice of it) keeps `owner` alive: numpy's base chain ends at the ctypes
+    buffer object, which carries a reference to the owner, so the library block is only returned
+    to the pinned pool when the last view is gone."""
     if n == 0:
         return np.zeros(0, dtype)
     buf = (C.c_char * (n * dtype.itemsize)).from_address(C.addressof(ptr.contents))
+    buf._phy_owner = owner
     a = np.frombuffer(buf, dtype=dtype)
     a.flags.writeable = False
     return a
@@ -102,9 +106,30 @@ class PinnedBuffer:
             pass
 
 
+class _SerializedLib:
+    """The library as one Matcher sees it: every call holds the Matcher's lock, because a phy_ctx is
+    driven by one host thread at a time (include/phylign_cuda.h).  Lets a loader thread push the next
+    round's indexes between the match calls of the main thread."""
+
+    def __init__(self, L, lock):
+        self._L, self._lock = L, lock
+
+    def __getattr__(self, name):
+        fn = getattr(self._L, name)
+        lock = self._lock
+
+        def call(*args):
+            with lock:
+                return fn(*args)
+        setattr(self, name, call)
+        return call
+
+
 class Matcher:
     def __init__(self, device: int = 0, hbm_budget: int = 0):
-        self._L = _lib.load()
+        import threading
+        self._lock = threading.RLock()
+        self._L = _SerializedLib(_lib.load(), self._lock)
         self._ctx = C.c_void_p()
         _lib.check(self._L.phy_ctx_create(C.byref(self._ctx), device, hbm_budget))
         self.device = device
@@ -167,24 +192,35 @@ class Matcher:
         self.indexes[idx_id] = ResidentIndex(idx_id, batch, st.header)
         return idx_id
 
-    def load_indexes(self, paths, batches=None, workers: int = 4):
+    def load_indexes(self, paths, batches=None, workers: int = 4, keep_paths=None, active: bool = True):
         """Load several index files concurrently: one xz decoder process + one host thread per
         stream, chunks read straight into page-locked buffers and pushed under a lock (the
         library is driven by one thread at a time).  Decoding is the bottleneck (~0.3 GB/s per
         stream), so throughput scales with `workers` up to the host's cores.
+        keep_paths[i] (optional): also leave the decompressed stream there (written as .tmp, then
+        renamed) -- the file the reference's `decompress_cobs` rule produces (Snakefile:364-387).
+        active=False: the indexes stay out of phy_match_run until set_active_only() names them.
         Returns the index ids in the order of `paths`."""
         import threading
         from concurrent.futures import ThreadPoolExecutor
         batches = batches or [os.path.basename(str(p)).split(".cobs_classic")[0] for p in paths]
+        keep_paths = keep_paths or [None] * len(paths)
         lock = threading.Lock()
         chunk = 8 << 20
 
-        def one(path, batch):
+        def one(path, batch, keep):
             bufs = [PinnedBuffer(chunk), PinnedBuffer(chunk)]
+            tee = None
             with IndexStream(path, chunk_bytes=chunk) as st:
                 with lock:
                     idx_id = self._begin(batch, st.header)
+                    if not active:
+                        self._ck(self._L.phy_index_set_active(self._ctx, idx_id, 0))
                 try:
+                    if keep:
+                        os.makedirs(os.path.dirname(os.path.abspath(keep)), exist_ok=True)
+                        tee = open(keep + ".tmp", "wb")
+                        tee.write(st.header.to_bytes())
                     k = 0
                     for piece in st.body_chunks():
                         n = len(piece)
@@ -193,20 +229,42 @@ class Matcher:
                         b = bufs[k & 1]
                         k += 1
                         b.array[:n] = np.frombuffer(piece, dtype=np.uint8)
+                        if tee:
+                            tee.write(b.array[:n])
                         with lock:
                             self._ck(self._L.phy_index_push(self._ctx, idx_id, b.ptr, n))
                     with lock:
                         self._ck(self._L.phy_index_commit(self._ctx, idx_id))
+                    if tee:
+                        tee.close()
+                        tee = None
+                        os.replace(keep + ".tmp", keep)
                 except Exception:
                     with lock:
                         self._L.phy_index_evict(self._ctx, idx_id)
+                    if tee:
+                        tee.close()
+                    if keep and os.path.exists(keep + ".tmp"):
+                        os.unlink(keep + ".tmp")
                     raise
             with lock:
                 self.indexes[idx_id] = ResidentIndex(idx_id, batch, st.header)
             return idx_id
 
         with ThreadPoolExecutor(max_workers=max(1, workers)) as ex:
-            return list(ex.map(one, paths, batches))
+            return list(ex.map(one, paths, batches, keep_paths))
+
+    def set_active_only(self, idx_ids):
+        """Only these resident indexes take part in the following match_run calls."""
+        only = set(idx_ids)
+        for i in list(self.indexes):
+            self._ck(self._L.phy_index_set_active(self._ctx, i, int(i in only)))
+
+    def budget_bytes(self) -> int:
+        """HBM bytes this context may use in total (phy_ctx_create's hbm_budget, or what was free)."""
+        b = C.c_uint64()
+        self._ck(self._L.phy_ctx_budget(self._ctx, C.byref(b), None))
+        return b.value
 
     def load_index_bytes(self, raw: bytes, batch: str) -> int:
         hdr, body = parse_bytes(raw)
@@ -252,6 +310,28 @@ class Matcher:
         buf = C.create_string_buffer(n)
         self._ck(self._L.phy_index_download(self._ctx, idx_id, buf, n))
         return buf.raw
+
+    def download_index_into(self, idx_id, out):
+        """Packed body bytes of a resident index into `out` (PinnedBuffer or uint8 numpy array of
+        body_size bytes) -- no intermediate copies."""
+        n = self.indexes[idx_id].header.body_size
+        ptr = out.ptr if isinstance(out, PinnedBuffer) else out.ctypes.data
+        assert (out.nbytes if isinstance(out, PinnedBuffer) else out.size) >= n
+        self._ck(self._L.phy_index_download(self._ctx, idx_id, ptr, n))
+        return n
+
+    def write_index_file(self, idx_id, path, buf=None):
+        """Write a resident index as a `.cobs_classic` file (SURVEY Appendix A.1 layout: what
+        `xzcat {batch}.cobs_classic.xz` yields), tmp + rename."""
+        ix = self.indexes[idx_id]
+        n = ix.header.body_size
+        buf = buf if buf is not None else PinnedBuffer(n)
+        self.download_index_into(idx_id, buf)
+        tmp = f"{path}.tmp.{os.getpid()}"
+        with open(tmp, "wb") as f:
+            f.write(ix.header.to_bytes())
+            f.write(memoryview(buf.array if isinstance(buf, PinnedBuffer) else buf)[:n])
+        os.replace(tmp, path)
 
     def set_ranks(self, all_batches=None):
         """Upload the integer ranks behind the merge key (-kmers, batch, ref) of
@@ -331,7 +411,9 @@ class Matcher:
 
     def merged(self):
         """(offs[nq+1], cands structured array) of the cross-index top-N + ties merge.
-        Zero-copy views of pinned library memory, kept alive by the arrays' owner (`.base`)."""
+        Zero-copy views of pinned library memory; the arrays (and their slices) hold a reference
+        to the library block (see `_view`), so they stay valid after the next merged()/merge_host()
+        call.  `self._merged_owner` is the most recent block (used by the FASTA formatter)."""
         mp = C.POINTER(_lib.Merged)()
         self._ck(self._L.phy_merged_fetch(self._ctx, C.byref(mp)))
         owner = _Owned(mp, self._L.phy_merged_free)
@@ -339,7 +421,7 @@ class Matcher:
         nq = int(m.n_queries)
         offs = _view(m.offs, nq + 1, np.dtype("<u8"), owner)
         cands = _view(m.cands, int(offs[-1]), CAND_DT, owner)
-        self._merged_owner = owner      # valid until the next merged() call
+        self._merged_owner = owner
         return offs, cands
 
     def merge_host(self, offs: np.ndarray, cands: np.ndarray, top_n: int):
@@ -375,6 +457,11 @@ class Matcher:
     def gathered_bytes(self) -> int:
         b = C.c_uint64()
         self._ck(self._L.phy_last_gather_bytes(self._ctx, C.byref(b)))
+        return b.value
+
+    def gathered_bytes_of(self, idx_id) -> int:
+        b = C.c_uint64()
+        self._ck(self._L.phy_last_gather_bytes_of(self._ctx, idx_id, C.byref(b)))
         return b.value
 
     def set_option(self, name: str, value: int):

@@ -165,7 +165,7 @@ def test_config4_all_305_batch_shapes_and_cross_batch_merge(M):
             pq.append((qn, [(ref_of(oi.doc_names[d]), sc) for d, sc in hits]))
         per_batch.append((name, pq))
     want = filters.merge_closed_form([(qn, s) for qn, s in records], per_batch, keep)
-    from phylign_b200.cobs_text import format_filter_fasta
+    from text_twins import format_filter_fasta
     refs = {ix.batch_rank: [ref_of(n) for n in ix.doc_names] for ix in M.indexes.values()}
     assert format_filter_fasta(records, offs, cands, refs) == want
     assert len(cands) >= 24 * keep

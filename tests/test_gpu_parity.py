@@ -64,7 +64,7 @@ def _check_against_oracle(m, idx_id, oidx, records, threshold, top_n, floor_mode
 
 # --------------------------------------------------------------------------- golden vectors
 def test_golden_cobs_text_and_match_files(M, golden_queries):
-    from phylign_b200.cobs_text import format_cobs_text
+    from text_twins import format_cobs_text
     _evict_all(M)
     ids = {b: M.load_index(os.path.join(H.GOLDEN, f"{b}.cobs_classic.xz")) for b in H.GOLDEN_BATCHES}
     M.set_queries(golden_queries)
@@ -81,7 +81,7 @@ def test_golden_cobs_text_and_match_files(M, golden_queries):
 def test_golden_filter_fasta(M, golden_queries):
     """bit-exact intermediate/04_filter content vs the unmodified filter_queries.py."""
     from phylign_b200.cobs_index import ref_of
-    from phylign_b200.cobs_text import format_filter_fasta
+    from text_twins import format_filter_fasta
     _evict_all(M)
     # load in non-sorted order: the merge must not depend on it (filter_queries.py:135)
     for b in reversed(H.GOLDEN_BATCHES):
@@ -284,7 +284,7 @@ def test_result_buffers_regrow_and_rerun(golden_queries):
     code = (
         "import os, sys; sys.path.insert(0, %r)\n"
         "from phylign_b200.matcher import Matcher\n"
-        "from phylign_b200.cobs_text import format_cobs_text\n"
+        "from tests.text_twins import format_cobs_text\n"
         "from tests import helpers as H\n"
         "m = Matcher(0); i = m.load_index(os.path.join(H.GOLDEN, 'aaa__01.cobs_classic.xz'))\n"
         "qs = H.read_fasta(os.path.join(H.GOLDEN, 'queries.fa')); m.set_queries(qs)\n"

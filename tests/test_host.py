@@ -92,7 +92,7 @@ def test_fasta_readers(tmp_path):
 
 
 def test_text_formatters_with_synthetic_results():
-    from phylign_b200.cobs_text import format_cobs_text, format_filter_fasta
+    from text_twins import format_cobs_text, format_filter_fasta
     from phylign_b200.matcher import CAND_DT, HIT_DT, UNIT_DT, MatchResult, ResidentIndex
     from phylign_b200.cobs_index import ClassicHeader
     hdr = ClassicHeader(31, 1, 3, 10, 1, ["zz9_SAMEA3", "ab1_SAMEA1", "qq2_SAMEA2"])
@@ -125,7 +125,7 @@ def test_cli_postprocess_stream_equals_reference_output(keep):
 
 
 def test_cli_parse_match_file_rules(tmp_path):
-    from phylign_b200.cli import parse_match_file
+    from text_twins import parse_match_file
     p = os.path.join(H.GOLDEN, "n3", "aaa__01____queries.gz")
     blocks = parse_match_file(p)
     ref = H.read_fasta(os.path.join(H.GOLDEN, "queries.fa"))
@@ -171,8 +171,8 @@ def test_c_formatters_equal_python_formatters():
     import ctypes as C
     from phylign_b200 import _lib
     from phylign_b200.cobs_index import ClassicHeader
-    from phylign_b200.cobs_text import (format_cobs_text, format_cobs_text_fast, format_filter_fasta,
-                                        format_filter_fasta_fast)
+    from phylign_b200.cobs_text import format_cobs_text_fast, format_filter_fasta_fast
+    from text_twins import format_cobs_text, format_filter_fasta
     from phylign_b200.matcher import CAND_DT, HIT_DT, UNIT_DT, MatchResult, ResidentIndex
     import random
     rnd = random.Random(3)
@@ -331,7 +331,8 @@ def test_header_roundtrip_property():
 def test_native_match_file_parser_equals_python_parser(tmp_path):
     """phy_parse_match_text (C++) == the line-by-line Python restatement of filter_queries.py:27-66,
     on the golden match files and on malformed inputs (same inputs rejected)."""
-    from phylign_b200.cli import parse_match_file, parse_match_file_native
+    from phylign_b200.cli import parse_match_file_native
+    from text_twins import parse_match_file
     for keep in (1, 3, 100):
         for b in H.GOLDEN_BATCHES:
             p = os.path.join(H.GOLDEN, f"n{keep}", f"{b}____queries.gz")
@@ -357,3 +358,84 @@ def test_native_match_file_parser_equals_python_parser(tmp_path):
     assert parse_match_file(str(ok)) == [("q1", [("R1", 5), ("R0", 4)]), ("q2", [])]
     qn, fh, ri, rs, km = parse_match_file_native(str(ok))
     assert qn == ["q1", "q2"] and fh.tolist() == [0, 2, 2] and [rs[i] for i in ri] == ["R1", "R0"] and km.tolist() == [5, 4]
+
+
+def _fake_results(rnd, nq, idx_ids, n_docs, recs):
+    """(units, hits, n_kmers, _lib.Results) fabricated on the host (no GPU involved)."""
+    import ctypes as C
+    from phylign_b200 import _lib
+    from phylign_b200.matcher import HIT_DT, UNIT_DT
+    units, hits = [], []
+    for i in idx_ids:
+        for q in range(nq):
+            if rnd.random() < 0.3 and recs[q][1]:
+                k = rnd.randrange(1, 6)
+                units.append((q, i, k + rnd.randrange(3), k, len(hits)))
+                hits += [(rnd.randrange(n_docs), rnd.randrange(1, 99999)) for _ in range(k)]
+    ua, ha = np.array(units, dtype=UNIT_DT), np.array(hits, dtype=HIT_DT)
+    nk = np.zeros(nq, np.uint32)
+    r = _lib.Results(nq, len(idx_ids), len(ua), C.cast(ua.ctypes.data, C.POINTER(_lib.Unit)), len(ha),
+                     C.cast(ha.ctypes.data, C.POINTER(_lib.Hit)), C.cast(nk.ctypes.data, C.POINTER(C.c_uint32)), 0, 0)
+    return ua, ha, nk, r
+
+
+@pytest.mark.parametrize("nq,gz", [(50, 1), (20000, 1), (300, 0)])
+def test_native_match_file_writer_equals_python_twin(tmp_path, nq, gz):
+    """phy_write_match_blocks (threads + zlib, one gzip member per task) leaves files whose decompressed
+    content is the twin formatter's text, block after block; nothing is visible before commit()."""
+    import ctypes as C
+    import random
+    from phylign_b200.cobs_index import ClassicHeader
+    from phylign_b200.cobs_text import _cat
+    from phylign_b200.match_files import MatchFileSet
+    from phylign_b200.matcher import MatchResult, ResidentIndex
+    from text_twins import format_cobs_text
+    rnd = random.Random(nq)
+    n_docs = 41
+    names = [f"{rnd.randrange(10**6):06d}_ACC{d:04d}" for d in range(n_docs)]
+    ixs = {i: ResidentIndex(i, f"b__0{i}", ClassicHeader(31, 1, n_docs, 10, 1, names)) for i in (0, 3, 4)}
+    paths = {i: str(tmp_path / f"b__0{i}____q{'.gz' if gz else '.txt'}") for i in ixs}
+    fs = MatchFileSet(paths, ixs, gzip_level=gz, threads=5)
+    want = {i: "" for i in ixs}
+    for block in range(3):
+        recs = [(f"q{block}_{q} c", "ACGT" * 10) for q in range(nq if block != 1 else 7)]
+        ua, ha, nk, r = _fake_results(rnd, len(recs), list(ixs), n_docs, recs)
+        res = MatchResult(ua, ha, nk, len(recs), 0, 0)
+        hcat, hoffs = _cat([h for h, _ in recs])
+        fs.write_block(hcat, hoffs, C.pointer(r))
+        for i in ixs:
+            want[i] += format_cobs_text(recs, res, ixs[i], strip_prefix=True)
+    assert not any(os.path.exists(p) for p in paths.values())
+    fs.commit()
+    for i, p in paths.items():
+        got = (gzip.open(p, "rt") if gz else open(p)).read()
+        assert got == want[i]
+        assert fs.file_bytes[i] == os.path.getsize(p)
+    st = fs.stats_dict()
+    assert st["header_lines"] == 3 * (2 * nq + 7) and st["text_bytes"] == sum(len(w) for w in want.values())
+    assert not [f for f in os.listdir(tmp_path) if ".tmp." in f]
+    # an aborted set leaves nothing behind; an empty committed gzip file is a valid gzip stream
+    fs2 = MatchFileSet({0: str(tmp_path / "x.gz")}, ixs, gzip_level=1)
+    fs2.abort()
+    assert not os.path.exists(tmp_path / "x.gz") and not [f for f in os.listdir(tmp_path) if ".tmp." in f]
+    fs3 = MatchFileSet({0: str(tmp_path / "e.gz")}, ixs, gzip_level=1)
+    fs3.commit()
+    assert gzip.open(tmp_path / "e.gz").read() == b""
+
+
+def test_view_keeps_owner_alive():
+    """Result arrays (and slices of them) hold the library block; it is released with the last view."""
+    import ctypes as C
+    import gc
+    from phylign_b200.matcher import HIT_DT, _Owned, _view
+    raw = (C.c_char * 64)()
+    freed = []
+    owner = _Owned(C.cast(raw, C.POINTER(C.c_char)), lambda p: freed.append(1))
+    a = _view(C.cast(raw, C.POINTER(C.c_char)), 4, HIT_DT, owner)
+    part = a[1:3]
+    del owner, a
+    gc.collect()
+    assert not freed
+    del part
+    gc.collect()
+    assert freed == [1]

@@ -16,7 +16,7 @@ root, rank, world, idfile, keep, out = sys.argv[1], int(sys.argv[2]), int(sys.ar
 sys.path.insert(0, root)
 from phylign_b200.matcher import Matcher, nccl_unique_id
 from phylign_b200.cobs_index import ref_of
-from phylign_b200.cobs_text import format_filter_fasta
+from tests.text_twins import format_filter_fasta
 from tests import helpers as H
 if rank == 0:
     with open(idfile + ".tmp", "wb") as f: f.write(nccl_unique_id())

@@ -196,3 +196,34 @@ def test_synth_spec_is_deterministic():
     r = oracle.synth_read([s], 1, 3, 150, random_q8=0, err_q16=0)
     gs = [oracle.synth_genome(s, d).decode() for d in range(40)]
     assert any(r.decode() in g or H.revcomp(r.decode()) in g for g in gs)
+
+
+def test_avx2_counting_equals_sse2_and_bit_loop():
+    """The 256-bit counting kernel (CPU-baseline option) gives the scores of the SSE2 (cobs-shape) one."""
+    import random
+    rnd = random.Random(11)
+    docs = [bytes(rnd.choice(b"ACGT") for _ in range(400)) for _ in range(300)]   # 300 docs: 38-B rows (ragged slices)
+    idx = oracle.OracleIndex.construct(docs)
+    reads = [docs[d][10:250] for d in (0, 17, 299)] + [bytes(rnd.choice(b"ACGT") for _ in range(120))]
+    want = [idx.scores(r)[1] for r in reads]
+    try:
+        for avx in (False, True):
+            mode = oracle.set_simd(avx)
+            for r, w in zip(reads, want):
+                for threads in (1, 3):
+                    assert (idx.scores(r, sliced=True, threads=threads)[1] == w).all(), (mode, threads)
+    finally:
+        oracle.set_simd(False)
+
+
+def test_oracle_cli_thread_layouts_print_the_same_text(tmp_path):
+    """cobs_oracle query: queries-over-threads (default for -T > 1) == slices-over-threads == serial."""
+    import subprocess
+    idxp = os.path.join(tmp_path, "i.cobs_classic")
+    open(idxp, "wb").write(H.golden_index_bytes("bbb__01"))
+    q = os.path.join(H.GOLDEN, "queries.fa")
+    outs = [subprocess.run([oracle.CLI_PATH, "query", "-t", "0.7", "-T", t, "-i", idxp, "-f", q] + extra,
+                           capture_output=True, text=True, check=True).stdout
+            for t, extra in (("1", []), ("4", []), ("4", ["--threads-over-slices"]), ("4", ["--avx2"]))]
+    assert outs[0] == H.golden_cobs_text("bbb__01")
+    assert outs[1] == outs[0] and outs[2] == outs[0] and outs[3] == outs[0]
