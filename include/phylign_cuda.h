@@ -190,6 +190,31 @@ typedef struct phy_match_text {
 int phy_parse_match_text(const char* text, uint64_t len, phy_match_text** out);
 void phy_match_text_free(phy_match_text* r);
 
+/* ------------------------------------------------------------------ query files
+ * `cobs query -f` record rules (the reader behind run_cobs_streaming.sh:24-29):
+ * '>' or ';' opens a record, sequence lines are concatenated, empty lines skipped, records without
+ * sequence dropped.  Flat arrays, no per-record objects: seqs/soffs go to phy_queries_set as they are
+ * (seqs is page-locked when a GPU is present), headers/hoffs to the text writers.  name_len[q] = length
+ * of the query name (header up to the first blank, filter_queries.py:59,80).  simple != 0: plain '>'
+ * FASTA for which readfq (filter_queries.py:69-102) yields the same records.  Host only. */
+typedef struct phy_fasta {
+    uint32_t n;
+    uint8_t simple, seqs_pinned;
+    char* seqs;        uint64_t* soffs;    /* [n+1] */
+    char* headers;     uint64_t* hoffs;    /* [n+1] header lines without their first character */
+    uint32_t* name_len;                    /* [n] */
+} phy_fasta;
+int phy_fasta_read(const char* path, phy_fasta** out);
+void phy_fasta_free(phy_fasta* f);
+/* filter_queries.py:152-156,195-199 output written straight to `final_path` (tmp + rename):
+ * ">{qname} {ref,ref,...}\n{seq}\n" per query of `m`; qname = headers[hoffs[q] .. +name_len[q]).
+ * ref_names/ref_offs/ref_counts as in phy_format_filter_fasta. */
+int phy_write_filter_fasta(const char* final_path, const phy_merged* m, const char* headers,
+                           const uint64_t* hoffs, const uint32_t* name_len, const char* seqs,
+                           const uint64_t* soffs, uint32_t n_batches, const char* const* ref_names,
+                           const uint64_t* const* ref_offs, const uint32_t* ref_counts,
+                           uint64_t* file_bytes /* may be NULL */);
+
 /* -------------------------------------------------------------- match-file writer
  * The tail of the reference's per-batch pipeline, `... | postprocess_cobs.py -n N | gzip --fast >
  * intermediate/03_match/{batch}____{qfile}.gz` (Snakefile:425-427,467-469,482-484), for the results of

@@ -245,16 +245,47 @@ orc_index* orc_index_parse(const uint8_t* buf, uint64_t len) {
     return idx;
 }
 
+/* `cobs query --load-complete`: the whole index is read into RAM once.  Header from the first
+ * bytes, then the body straight into its final place (no intermediate copy). */
 orc_index* orc_index_read(const char* path) {
     FILE* f = fopen(path, "rb");
     if (!f) return NULL;
     fseek(f, 0, SEEK_END);
     long n = ftell(f);
     fseek(f, 0, SEEK_SET);
-    uint8_t* buf = (uint8_t*)malloc(n > 0 ? (size_t)n : 1);
     orc_index* idx = NULL;
-    if (buf && fread(buf, 1, (size_t)n, f) == (size_t)n) idx = orc_index_parse(buf, (uint64_t)n);
-    free(buf);
+    uint8_t head[47];
+    if (n < 47 + 13 || fread(head, 1, 47, f) != 47 || memcmp(head, MAGIC0, 5) || memcmp(head + 5, MAGIC1, 13)) {
+        fclose(f);
+        return NULL;
+    }
+    uint32_t version, k, nd; uint8_t canon; uint64_t sig, nh;
+    memcpy(&version, head + 18, 4); memcpy(&k, head + 22, 4); canon = head[26];
+    memcpy(&nd, head + 27, 4); memcpy(&sig, head + 31, 8); memcpy(&nh, head + 39, 8);
+    if (version != 1) { fclose(f); return NULL; }
+    char** names = (char**)calloc(nd ? nd : 1, sizeof(char*));
+    char* line = NULL; size_t cap = 0; int ok = 1;
+    uint64_t hdr = 47;
+    for (uint32_t d = 0; d < nd && ok; d++) {
+        ssize_t got = getline(&line, &cap, f);
+        if (got <= 0 || line[got - 1] != '\n') { ok = 0; break; }
+        hdr += (uint64_t)got;
+        names[d] = strndup(line, (size_t)got - 1);
+    }
+    free(line);
+    char endm[13];
+    if (ok && (fread(endm, 1, 13, f) != 13 || memcmp(endm, MAGIC1, 13))) ok = 0;
+    hdr += 13;
+    uint64_t row_size = ((uint64_t)nd + 7) / 8;
+    if (ok && (uint64_t)n - hdr == sig * row_size) {
+        idx = orc_index_new(k, canon, nd, sig, nh, (const char* const*)names);
+        if (idx && sig * row_size > 0 && fread(idx->body, 1, sig * row_size, f) != sig * row_size) {
+            orc_index_free(idx);
+            idx = NULL;
+        }
+    }
+    for (uint32_t d = 0; d < nd; d++) free(names[d]);
+    free(names);
     fclose(f);
     return idx;
 }

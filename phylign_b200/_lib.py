@@ -60,6 +60,13 @@ class MatchText(C.Structure):
                 ("kmers", C.POINTER(C.c_uint32))]
 
 
+class Fasta(C.Structure):
+    _fields_ = [("n", C.c_uint32), ("simple", C.c_uint8), ("seqs_pinned", C.c_uint8),
+                ("seqs", C.c_void_p), ("soffs", C.POINTER(C.c_uint64)),
+                ("headers", C.c_void_p), ("hoffs", C.POINTER(C.c_uint64)),
+                ("name_len", C.POINTER(C.c_uint32))]
+
+
 class MFileJob(C.Structure):
     _fields_ = [("file", C.c_void_p), ("idx_id", C.c_uint32), ("n_docs", C.c_uint32),
                 ("names", C.c_char_p), ("noffs", C.c_void_p)]
@@ -120,10 +127,15 @@ PROTOTYPES = {
     "phy_text_free": (None, [C.c_void_p]),
     "phy_parse_match_text": (C.c_int, [C.c_char_p, C.c_uint64, C.POINTER(C.POINTER(MatchText))]),
     "phy_match_text_free": (None, [C.POINTER(MatchText)]),
+    "phy_fasta_read": (C.c_int, [C.c_char_p, C.POINTER(C.POINTER(Fasta))]),
+    "phy_fasta_free": (None, [C.POINTER(Fasta)]),
+    "phy_write_filter_fasta": (C.c_int, [C.c_char_p, C.POINTER(Merged), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.POINTER(C.c_uint64)]),
     "phy_mfile_open": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]),
     "phy_mfile_commit": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "phy_mfile_abort": (None, [C.c_void_p]),
-    "phy_write_match_blocks": (C.c_int, [C.POINTER(Results), C.POINTER(MFileJob), C.c_uint32, C.c_char_p, C.c_void_p,
+    "phy_write_match_blocks": (C.c_int, [C.POINTER(Results), C.POINTER(MFileJob), C.c_uint32, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_int, C.c_int, C.POINTER(WriteStats)]),
     "phy_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "phy_nccl_init": (C.c_int, [_P, C.c_void_p, C.c_int, C.c_int]),

@@ -191,16 +191,20 @@ def _parsed_pieces(match_fns, qid, brank, log):
     return pieces, refs_by_rank
 
 
-def _final_merge(m, queries, pieces, refs_by_rank, keep: int) -> str:
-    """Global top-N + ties over candidate pieces (filter_queries.py:123-150) on the GPU."""
+def _merge_pieces(m, nq: int, pieces, keep: int):
+    """Global top-N + ties over candidate pieces (filter_queries.py:123-150) on the GPU; the result is
+    the Matcher's current merged list."""
     from .matcher import CAND_DT
-    nq = len(queries)
     qs = np.concatenate([p[0] for p in pieces]) if pieces else np.zeros(0, np.int64)
     cs = np.concatenate([p[1] for p in pieces]) if pieces else np.zeros(0, CAND_DT)
     order = np.argsort(qs, kind="stable")
     offs = np.zeros(nq + 1, dtype=np.uint64)
     offs[1:] = np.cumsum(np.bincount(qs, minlength=nq), dtype=np.uint64)
-    m.merge_host(offs, cs[order], keep)
+    return m.merge_host(offs, cs[order], keep)
+
+
+def _final_merge(m, queries, pieces, refs_by_rank, keep: int) -> str:
+    _merge_pieces(m, len(queries), pieces, keep)
     return format_filter_fasta_fast(list(queries.items()), m._merged_owner.ptr, refs_by_rank).decode()
 
 
@@ -357,7 +361,7 @@ def cmd_match_db(a):
     with open(a.batches) as f:
         batches = sorted(filter(len, map(str.strip, f)))      # Snakefile:32-34
     with tm.span("read_queries_s"):
-        records = fasta.read_cobs_records(a.q)
+        qf = fasta.QueryFile(a.q)                             # flat arrays: no per-record Python objects
     qfile = a.qfile or os.path.splitext(os.path.basename(a.q))[0]
     os.makedirs(a.match_dir, exist_ok=True)
     sizes = {}
@@ -410,12 +414,14 @@ def cmd_match_db(a):
         shard, n_shards = (int(x) for x in a.shard.split("/"))
     if nccl:
         shard, n_shards = rank, world
-    total_bases = sum(len(s) for _, s in records)
+    total_bases = qf.total_bases
+    t_ctx = time.perf_counter()
     with Matcher(rank if nccl else a.device, a.hbm_budget) as m:
+        tm.add("ctx_create_s", time.perf_counter() - t_ctx)
         # HBM left for indexes = the context's budget minus the working set of one query block
         # (hashes 8 B per base, sequence 1 B, unit tables, result/merge buffers)
         block_bases = min(total_bases, a.query_block_bases)
-        working = 10 * block_bases + 24 * len(records) + (2 << 30)
+        working = 10 * block_bases + 24 * qf.n + (2 << 30)
         free_for_indexes = max(0, m.budget_bytes() - working)
         budget = min(a.round_bytes, free_for_indexes) if a.round_bytes else int(free_for_indexes * 0.95)
         try:
@@ -432,10 +438,21 @@ def cmd_match_db(a):
         if a.filter_out and not want_filter:
             _die("--filter-out needs all batches: use --gpus N, or run `filter` over the match files of all shards")
         collect = want_filter and (not nccl or rank == 0)     # who assembles 04_filter
-        queries, qid = _load_filter_queries(a.q) if collect else ({}, {})
         brank = sharding.global_batch_ranks(batches)
-        rec2qid = np.array([qid[h.split(" ")[0]] for h, _ in records], dtype=np.int64) if collect else None
-        identity = collect and len(queries) == len(records) and bool((rec2qid == np.arange(len(records))).all())
+        # the merge works on the query dict of filter_queries.py:163-176 (readfq names, duplicates
+        # collapsed).  For plain FASTA with unique names that is the record list itself.
+        qnames = queries = qid = rec2qid = None
+        identity = False
+        if collect:
+            with tm.span("query_names_s"):
+                qnames = qf.names()
+                identity = qf.simple and len(set(qnames)) == qf.n
+                if not identity:
+                    queries, qid = _load_filter_queries(a.q)
+                    rec2qid = np.array([qid[nm] for nm in qnames], dtype=np.int64)
+                else:
+                    qid = {nm: i for i, nm in enumerate(qnames)} if merged_inputs else None
+        n_merge_queries = qf.n if identity else (len(queries) if queries is not None else 0)
         pieces, refs_by_rank = [], {}
         if collect and merged_inputs:
             with tm.span("parse_existing_s"):
@@ -447,10 +464,9 @@ def cmd_match_db(a):
                     f.write(nccl_unique_id())
                 os.replace(id_file + ".tmp", id_file)
             m.nccl_init(_wait_for_file(id_file, float(os.environ.get("PHYLIGN_NCCL_ID_TIMEOUT", 300))), rank, world)
-        blocks = list(query_blocks(records, a.query_block_bases))
-        block_hdrs = [_cat([h for h, _ in blk]) for _, blk in blocks]
+        blocks = qf.block_ranges(a.query_block_bases)
         wstats, gpu_phase_ms, gathered_total, n_writer_blocks = [], np.zeros(3), 0, 0
-        direct_merged = None                                   # (owner ptr) when one device merge is already final
+        direct_merged = direct_arrays = None                   # set when one device merge is already the final answer
         bg = _TPE(max_workers=1)                               # the writer thread (format + gzip + append)
         loader = _TPE(max_workers=1)                           # next round's indexes (--overlap-rounds)
         rounds = [sorted(x.name for x in rnd[shard]) for rnd in plan.rounds]
@@ -475,8 +491,9 @@ def cmd_match_db(a):
                     pending_load = loader.submit(load_round, rounds[ri + 1])
                 if not mine and not (nccl and want_filter):
                     continue                                   # (under NCCL every rank joins every merge)
-                m.set_ranks(batches)
-                m.set_active_only(loaded)
+                with tm.span("set_ranks_s"):
+                    m.set_ranks(batches)
+                    m.set_active_only(loaded)
                 fs = MatchFileSet({idx: os.path.join(a.match_dir, f"{m.indexes[idx].batch}____{qfile}.gz")
                                    for idx in loaded}, m.indexes, gzip_level=1, threads=a.write_threads)
                 n_hit_queries = {idx: 0 for idx in loaded}
@@ -484,10 +501,10 @@ def cmd_match_db(a):
                 round_gpu_ms, round_bytes_by_idx = 0.0, {idx: 0 for idx in loaded}
                 fut = None
                 try:
-                    for bi, (q0, block) in enumerate(blocks):
+                    for bi, (q0, q1) in enumerate(blocks):
                         if len(blocks) > 1 or ri == 0:          # one block: queries stay resident across rounds
                             with tm.span("set_queries_s"):
-                                m.set_queries(block)
+                                m.set_queries_raw(qf.seqs, qf.soffs[q0:q1 + 1])
                         with tm.span("gpu_match_s"):
                             m.match_run(a.t, top_n=a.n, floor_mode=a.floor, merge_top_n=a.n if want_filter else 0)
                         ph = m.phase_ms()
@@ -503,18 +520,18 @@ def cmd_match_db(a):
                         if fut is not None:                     # at most one block in flight behind the GPU
                             with tm.span("writer_wait_s"):
                                 fut.result()
-                        hcat, hoffs = block_hdrs[bi]
-                        fut = bg.submit(lambda r=res, hc=hcat, ho=hoffs: fs.write_block(hc, ho, r._owner.ptr))
+                        fut = bg.submit(lambda r=res, ho=qf.hoffs[q0:q1 + 1]: fs.write_block(qf.headers, ho, r._owner.ptr))
                         n_writer_blocks += 1
                         if collect:                             # this block's top-N + ties per query and round
                             with tm.span("fetch_merged_s"):
                                 moffs, mc = m.merged()
                             if identity and len(rounds) == 1 and len(blocks) == 1 and not pieces:
                                 direct_merged = m._merged_owner   # already the global answer: no host re-merge
+                                direct_arrays = (moffs, mc)
                             else:
-                                q_of = q0 + np.repeat(np.arange(len(block), dtype=np.int64),
+                                q_of = q0 + np.repeat(np.arange(q1 - q0, dtype=np.int64),
                                                       np.diff(moffs.astype(np.int64)))
-                                pieces.append((rec2qid[q_of], np.array(mc)))
+                                pieces.append((q_of if identity else rec2qid[q_of], np.array(mc)))
                         elif nccl and want_filter:
                             m.merged()                          # non-holders still take part in the fetch
                     if fut is not None:
@@ -532,7 +549,7 @@ def cmd_match_db(a):
                     raise
                 wstats.append(fs.stats_dict())
                 round_wall = time.perf_counter() - round_t0
-                kmers = sum(max(len(s) - 30, 0) for _, s in records)
+                kmers = int(np.maximum(np.diff(qf.soffs.astype(np.int64)) - 30, 0).sum())
                 round_alg = sum((m.indexes[i].header.n_docs + 7) // 8 for i in loaded) or 1
                 for idx in loaded:
                     ix = m.indexes[idx]
@@ -568,19 +585,23 @@ def cmd_match_db(a):
                 if brank[b] not in refs_by_rank:
                     refs_by_rank[brank[b]] = [_ref_of(n) for n in headers_of[b].doc_names]
         if collect:
+            os.makedirs(os.path.dirname(os.path.abspath(a.filter_out)), exist_ok=True)
             with tm.span("final_merge_s"):
-                if direct_merged is not None:
-                    fa = format_filter_fasta_fast(list(queries.items()), direct_merged.ptr, refs_by_rank)
-                else:
-                    fa = _final_merge(m, queries, pieces, refs_by_rank, a.n).encode()
+                if direct_merged is None:
+                    direct_arrays = _merge_pieces(m, n_merge_queries, pieces, a.n)
+                    direct_merged = m._merged_owner
             with tm.span("write_filter_s"):
-                os.makedirs(os.path.dirname(os.path.abspath(a.filter_out)), exist_ok=True)
-                _atomic_write(a.filter_out, fa, gz=False)
+                if identity:                                  # flat arrays straight into the file (tmp + rename)
+                    from .cobs_text import write_filter_fasta_native
+                    write_filter_fasta_native(a.filter_out, direct_merged.ptr, qf, refs_by_rank)
+                else:
+                    _atomic_write(a.filter_out, format_filter_fasta_fast(list(queries.items()), direct_merged.ptr,
+                                                                         refs_by_rank), gz=False)
             if a.bucket_dir:      # per-batch "reference -> queries to align" tables for stage 05
                 from .cobs_text import candidate_buckets, format_bucket_tsv
                 with tm.span("buckets_s"):
-                    moffs, mc = m.merged()
-                    buckets = candidate_buckets(list(queries), moffs, mc, refs_by_rank)
+                    moffs, mc = direct_arrays
+                    buckets = candidate_buckets(qnames if identity else list(queries), moffs, mc, refs_by_rank)
                     os.makedirs(a.bucket_dir, exist_ok=True)
                     for b in batches:
                         _atomic_write(os.path.join(a.bucket_dir, f"{b}____{qfile}.candidates.tsv"),
@@ -591,9 +612,10 @@ def cmd_match_db(a):
                    "writer": dict(w, threads=wstats[0]["threads"] if wstats else 0, blocks=n_writer_blocks),
                    "gpu_phase_ms_hash_gather_merge": [round(float(x), 3) for x in gpu_phase_ms],
                    "gathered_bytes": int(gathered_total), "rounds": len(rounds), "query_blocks": len(blocks),
-                   "overlap_rounds": bool(overlap), "n_queries": len(records), "bases": int(total_bases),
+                   "overlap_rounds": bool(overlap), "n_queries": qf.n, "bases": int(total_bases),
                    "n_batches": len(todo), "rank": max(rank, 0), "world": world,
-                   "direct_device_merge": direct_merged is not None}
+                   "direct_device_merge": bool(identity and len(rounds) == 1 and len(blocks) == 1),
+                   "native_filter_writer": bool(identity)}
             tmp = a.timing_json + f".tmp.{os.getpid()}"
             with open(tmp, "w") as f:
                 json.dump(out, f)

@@ -73,6 +73,31 @@ def format_filter_fasta_fast(records, merged_ptr, ref_names_by_rank) -> bytes:
         L.phy_text_free(out)
 
 
+def _ref_tables(ref_names_by_rank):
+    import ctypes as C
+    nb = (max(ref_names_by_rank) + 1) if ref_names_by_rank else 0
+    cats = [_cat(ref_names_by_rank.get(b, [])) for b in range(nb)]
+    name_ptrs = (C.c_char_p * max(nb, 1))(*[c for c, _ in cats])
+    off_ptrs = (C.c_void_p * max(nb, 1))(*[o.ctypes.data for _, o in cats])
+    counts = np.array([len(ref_names_by_rank.get(b, [])) for b in range(nb)] or [0], dtype=np.uint32)
+    return nb, cats, name_ptrs, off_ptrs, counts
+
+
+def write_filter_fasta_native(path, merged_ptr, qf, ref_names_by_rank) -> int:
+    """intermediate/04_filter/{qfile}.fa written by the library (phy_write_filter_fasta) from the flat
+    arrays of a fasta.QueryFile: no Python strings, tmp + rename.  Returns the file size."""
+    import ctypes as C
+    import os
+    from . import _lib
+    L = _lib.load()
+    nb, cats, name_ptrs, off_ptrs, counts = _ref_tables(ref_names_by_rank)
+    n = C.c_uint64()
+    _lib.check(L.phy_write_filter_fasta(os.fsencode(path), merged_ptr, qf.headers.ctypes.data, qf.hoffs.ctypes.data,
+                                        qf.name_len.ctypes.data, qf.seqs.ctypes.data, qf.soffs.ctypes.data, nb,
+                                        name_ptrs, off_ptrs, counts.ctypes.data, C.byref(n)))
+    return n.value
+
+
 # ---- 04 -> 05 hand-off (SURVEY.md 8(f) f4) -------------------------------------------------------
 def candidate_buckets(qnames, offs, cands, ref_names_by_rank):
     """{batch_rank: [(ref, [qname, ...])]}: for every reference that is a candidate of at least one

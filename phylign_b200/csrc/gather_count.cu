@@ -1176,8 +1176,13 @@ int phy_launch_gather(phy_ctx* ctx, const phy_match_params* p) {
     }
 
     uint64_t units_cap = ctx->d_units.cap, hits_cap = ctx->d_hits.cap;
-    if (units_cap < 4096) units_cap = 1 << 16;
-    if (hits_cap < 4096) hits_cap = 1 << 20;
+    // first sizing guess for a new workload (an overflow is still caught: the pass reports the needed
+    // sizes and is rerun): one unit per 8 (query, index) cells, 64 kept hits per query
+    uint64_t n_active_idx = 0;
+    for (auto& ix : ctx->idx) n_active_idx += ix.alive && ix.committed && ix.active;
+    if (units_cap < 4096)
+        units_cap = std::min<uint64_t>(std::max<uint64_t>(1u << 16, (uint64_t)ctx->nq * n_active_idx / 8), 1ull << 24);
+    if (hits_cap < 4096) hits_cap = std::min<uint64_t>(std::max<uint64_t>(1u << 20, 64ull * ctx->nq), 1ull << 27);
     if (const char* e = getenv("PHY_TEST_TINY_CAPS")) {  // tests: force the overflow -> regrow -> rerun path
         if (atoi(e) && !ctx->d_units.p) { units_cap = 4; hits_cap = 4; }
     }

@@ -10,6 +10,7 @@ first space).
 from __future__ import annotations
 
 import gzip
+import os
 
 
 def _open_text(path):
@@ -91,3 +92,92 @@ def fix_query_seq(seq) -> str:
 def fix_query_file(path) -> str:
     """The content of intermediate/00_queries_preprocessed/{qfile}.fa for one input file."""
     return "".join(f">{name}\n{fix_query_seq(seq)}\n" for name, seq in read_fastx(path))
+
+
+# ---- flat-array query file (native reader) -----------------------------------------------------------
+class QueryFile:
+    """A query FASTA as four flat arrays (phy_fasta_read, include/phylign_cuda.h): `seqs`/`soffs`
+    (concatenated bases, page-locked when a GPU is present) and `headers`/`hoffs` (header lines
+    without '>'), plus `name_len` (query name = header up to the first blank).  Same record rules as
+    read_cobs_records.  Gzipped input goes through the Python reader and is packed the same way."""
+
+    def __init__(self, path):
+        import ctypes as C
+        import numpy as np
+        from . import _lib
+        self._fp = None
+        self.path = str(path)
+        if self.path.endswith(".gz"):
+            recs = read_cobs_records(self.path)
+            hs = [h.encode() for h, _ in recs]
+            ss = [s.encode() for _, s in recs]
+            self.n = len(recs)
+            self.seqs = np.frombuffer(b"".join(ss) + b"\0", dtype=np.uint8)
+            self.headers = np.frombuffer(b"".join(hs) + b"\0", dtype=np.uint8)
+            self.soffs = np.zeros(self.n + 1, np.uint64)
+            self.hoffs = np.zeros(self.n + 1, np.uint64)
+            if recs:
+                self.soffs[1:] = np.cumsum([len(s) for s in ss], dtype=np.uint64)
+                self.hoffs[1:] = np.cumsum([len(h) for h in hs], dtype=np.uint64)
+            self.name_len = np.array([len(h.split(b" ")[0]) for h in hs], dtype=np.uint32)
+            self.simple = False
+            return
+        L = _lib.load()
+        fp = C.POINTER(_lib.Fasta)()
+        rc = L.phy_fasta_read(os.fsencode(self.path), C.byref(fp))
+        if rc != 0:
+            raise OSError(L.phy_last_error(None).decode())
+        self._fp, self._L = fp, L
+        f = fp.contents
+        self.n = int(f.n)
+        self.simple = bool(f.simple)
+
+        def view(addr, nbytes, dt):
+            if nbytes == 0:
+                return np.zeros(0, dt)
+            buf = (C.c_char * nbytes).from_address(addr)
+            buf._phy_owner = self          # the arrays keep the native block alive
+            return np.frombuffer(buf, dtype=dt)
+        self.soffs = view(C.addressof(f.soffs.contents), (self.n + 1) * 8, np.uint64)
+        self.hoffs = view(C.addressof(f.hoffs.contents), (self.n + 1) * 8, np.uint64)
+        self.name_len = view(C.addressof(f.name_len.contents), self.n * 4, np.uint32) if self.n else np.zeros(0, np.uint32)
+        self.seqs = view(f.seqs, int(self.soffs[-1]) + 1, np.uint8)
+        self.headers = view(f.headers, int(self.hoffs[-1]) + 1, np.uint8)
+
+    def __del__(self):
+        try:
+            if self._fp:
+                self._L.phy_fasta_free(self._fp)
+                self._fp = None
+        except Exception:
+            pass
+
+    @property
+    def total_bases(self) -> int:
+        return int(self.soffs[-1])
+
+    def header(self, q) -> str:
+        return bytes(self.headers[int(self.hoffs[q]):int(self.hoffs[q + 1])]).decode()
+
+    def names(self):
+        hb = bytes(self.headers)
+        ho, nl = self.hoffs.tolist(), self.name_len.tolist()
+        return [hb[ho[q]:ho[q] + nl[q]].decode() for q in range(self.n)]
+
+    def records(self):
+        """[(header, seq bytes)] -- the list form the older entry points take."""
+        hb, sb = bytes(self.headers), bytes(self.seqs)
+        ho, so = self.hoffs.tolist(), self.soffs.tolist()
+        return [(hb[ho[q]:ho[q + 1]].decode(), sb[so[q]:so[q + 1]]) for q in range(self.n)]
+
+    def block_ranges(self, max_bases: int):
+        """Consecutive [q0, q1) ranges of at most max_bases bases (at least one record each)."""
+        import numpy as np
+        out, q0 = [], 0
+        so = self.soffs
+        while q0 < self.n:
+            q1 = int(np.searchsorted(so, so[q0] + np.uint64(max_bases), "right")) - 1
+            q1 = min(self.n, max(q1, q0 + 1))
+            out.append((q0, q1))
+            q0 = q1
+        return out or [(0, 0)]

@@ -56,11 +56,17 @@ class MatchFileSet:
             jobs[j].names, jobs[j].noffs = ncat, noffs.ctypes.data
         self._jobs = jobs
 
-    def write_block(self, headers_cat: bytes, hoffs: np.ndarray, results_ptr, skip=None):
-        """Append the cobs text of one query block (headers of its records, in order) to every file."""
+    def write_block(self, headers_cat, hoffs: np.ndarray, results_ptr, skip=None):
+        """Append the cobs text of one query block to every file.  headers_cat: bytes or uint8 array with
+        the header lines; hoffs[nq+1]: where the headers of this block's records start in it."""
         if not self._files:
             return
-        _lib.check(self._L.phy_write_match_blocks(results_ptr, self._jobs, len(self._files), headers_cat,
+        if isinstance(headers_cat, np.ndarray):
+            haddr = headers_cat.ctypes.data
+        else:
+            haddr = C.cast(C.c_char_p(headers_cat), C.c_void_p).value
+        hoffs = np.ascontiguousarray(hoffs, dtype=np.uint64)
+        _lib.check(self._L.phy_write_match_blocks(results_ptr, self._jobs, len(self._files), haddr,
                                                   hoffs.ctypes.data, None if skip is None else skip.ctypes.data,
                                                   int(self.strip_prefix), self.threads, C.byref(self.stats)))
 

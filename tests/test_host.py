@@ -439,3 +439,62 @@ def test_view_keeps_owner_alive():
     del part
     gc.collect()
     assert freed == [1]
+
+
+def test_native_query_file_equals_python_reader(tmp_path):
+    """phy_fasta_read (flat arrays) == read_cobs_records, incl. the `simple` verdict that lets match-db
+    treat the record list as filter_queries.py's query dict."""
+    from phylign_b200.fasta import QueryFile, read_cobs_records, read_fastx
+    p = os.path.join(H.GOLDEN, "queries.fa")
+    q = QueryFile(p)
+    assert [(h, s.decode()) for h, s in q.records()] == read_cobs_records(p)
+    assert q.simple and q.names() == [n for n, _ in read_fastx(p)]
+    assert q.total_bases == sum(len(s) for _, s in read_cobs_records(p))
+    assert q.block_ranges(10 ** 9) == [(0, q.n)]
+    br = q.block_ranges(400)
+    assert br[0][0] == 0 and br[-1][1] == q.n and all(a[1] == b[0] for a, b in zip(br, br[1:]))
+    assert all(int(q.soffs[b] - q.soffs[a]) <= 400 or b == a + 1 for a, b in br)
+    cases = {"semi": ">a desc here\nACGT\nAC\n\n;empty\n>b\nGG\n>c x\nTT\n",
+             "crlf": ">a\r\nACGT\r\n>b\r\nGG\r\n", "noeol": ">a\nACGT\n>b\nGG", "fq": ">a\nAC\n+\nII\n",
+             "empty_rec": ">a\n>b\nGG\n", "tabname": ">a\tx y\nACGT\n", "plain": ">a x\nAC\nGT\n>b\nTT\n"}
+    for name, txt in cases.items():
+        f = tmp_path / f"{name}.fa"
+        f.write_bytes(txt.encode())
+        q = QueryFile(str(f))
+        assert [(h, s.decode()) for h, s in q.records()] == read_cobs_records(str(f)), name
+        assert q.simple == (name == "plain"), name
+    gz = tmp_path / "q.fa.gz"
+    with gzip.open(gz, "wt") as f:
+        f.write(cases["plain"])
+    qz = QueryFile(str(gz))
+    assert [(h, s.decode()) for h, s in qz.records()] == [("a x", "ACGT"), ("b", "TT")] and qz.names() == ["a", "b"]
+
+
+def test_native_filter_fasta_writer_equals_twin(tmp_path):
+    import ctypes as C
+    import random
+    from phylign_b200 import _lib
+    from phylign_b200.cobs_text import write_filter_fasta_native
+    from phylign_b200.fasta import QueryFile
+    from phylign_b200.matcher import CAND_DT
+    from text_twins import format_filter_fasta
+    rnd = random.Random(5)
+    nq, n_docs = 300, 23
+    fa = tmp_path / "q.fa"
+    fa.write_text("".join(f">q{q} comment {q}\n{'ACGT' * (1 + q % 7)}\n" for q in range(nq)))
+    qf = QueryFile(str(fa))
+    refs = {0: [f"SAM{d}" for d in range(n_docs)], 1: [], 2: [f"ERR{d}" for d in range(n_docs)]}
+    offs = np.zeros(nq + 1, np.uint64)
+    cands = []
+    for q in range(nq):
+        for _ in range(rnd.randrange(0, 6)):
+            cands.append((rnd.randrange(1, 500), rnd.choice([0, 2]), rnd.randrange(n_docs), 0))
+        offs[q + 1] = len(cands)
+    ca = np.array(cands, dtype=CAND_DT)
+    m = _lib.Merged(nq, C.cast(offs.ctypes.data, C.POINTER(C.c_uint64)), C.cast(ca.ctypes.data, C.POINTER(_lib.Cand)), 0)
+    out = tmp_path / "04" / "q.fa"
+    os.makedirs(out.parent)
+    n = write_filter_fasta_native(str(out), C.pointer(m), qf, refs)
+    want = format_filter_fasta([(f"q{q}", "ACGT" * (1 + q % 7)) for q in range(nq)], offs, ca, refs)
+    assert out.read_text() == want and n == len(want)
+    assert os.listdir(out.parent) == ["q.fa"]
