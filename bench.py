@@ -644,6 +644,7 @@ def run_match_db(workdir, tag, fasta, n_gpus, bases, hbm_budget_gb=0):
            "breakdown_s": dict(ph, process_start_and_exit=round(wall - timing["total_s"], 3), total_in_process=round(timing["total_s"], 3)),
            "host_s_outside_gpu_and_load": round(host_s, 3), "gpu_match_s": round(ph.get("gpu_match_s", 0.0), 3),
            "writer": timing["writer"], "direct_device_merge": timing.get("direct_device_merge"),
+           "gpu_phase_ms_hash_gather_merge": timing.get("gpu_phase_ms_hash_gather_merge"),
            "inputs": {"index_files": len(files), "index_bytes": sum(os.path.getsize(os.path.join(workdir, "cobs", f))
                                                                      for f in os.listdir(os.path.join(workdir, "cobs"))),
                       "query_fasta_bytes": os.path.getsize(fasta), "index_format": ".cobs_classic (decompressed, /dev/shm)"},

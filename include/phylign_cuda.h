@@ -193,8 +193,8 @@ void phy_match_text_free(phy_match_text* r);
 /* ------------------------------------------------------------------ query files
  * `cobs query -f` record rules (the reader behind run_cobs_streaming.sh:24-29):
  * '>' or ';' opens a record, sequence lines are concatenated, empty lines skipped, records without
- * sequence dropped.  Flat arrays, no per-record objects: seqs/soffs go to phy_queries_set as they are
- * (seqs is page-locked when a GPU is present), headers/hoffs to the text writers.  name_len[q] = length
+ * sequence dropped.  Flat arrays, no per-record objects: seqs/soffs go to phy_queries_set as they are,
+ * headers/hoffs to the text writers.  name_len[q] = length
  * of the query name (header up to the first blank, filter_queries.py:59,80).  simple != 0: plain '>'
  * FASTA for which readfq (filter_queries.py:69-102) yields the same records.  Host only. */
 typedef struct phy_fasta {
@@ -263,8 +263,9 @@ int phy_last_gather_bytes(phy_ctx* ctx, uint64_t* bytes);
 int phy_last_gather_bytes_of(phy_ctx* ctx, int idx_id, uint64_t* bytes);
 /* HBM accounting of this context: bytes it may use in total / bytes in use now */
 int phy_ctx_budget(phy_ctx* ctx, uint64_t* budget, uint64_t* used);
-/* tuning / A-B switches: "prune" 0|1 (exact threshold pruning, default 1),
- * "kernel_path" 1|2|3 (register-staged | bulk-copy ring | cp.async ring, default 3) */
+/* switches: "prune" 0|1 (exact threshold pruning, default 1; 0 for A/B measurements),
+ * "pinned_results" 0|1 (phy_results / phy_merged in page-locked memory from a reuse pool, default 1;
+ * 0 = plain host memory, cheaper for a single fetch) */
 int phy_ctx_set_option(phy_ctx* ctx, const char* name, int64_t value);
 /* write a buffer larger than L2 (bench hygiene between timed iterations) */
 int phy_flush_l2(phy_ctx* ctx);

@@ -431,7 +431,10 @@ def cmd_match_db(a):
                  f"block of {block_bases} bases: lower --query-block-bases or raise --hbm-budget)")
         overlap = a.overlap_rounds and len(plan.rounds) > 1
         if overlap:                                           # two rounds resident at once: halve the round size
-            plan = sharding.assign([shapes[b] for b in todo], n_shards, budget // 2)
+            try:
+                plan = sharding.assign([shapes[b] for b in todo], n_shards, budget // 2)
+            except ValueError:                                # a batch needs more than half: one round at a time
+                overlap = False
         # 04_filter is merged from the device results of every round (no re-parsing of what was just
         # written); only match files that already existed (--resume) are parsed
         want_filter = bool(a.filter_out) and (n_shards == 1 or nccl)
@@ -465,6 +468,9 @@ def cmd_match_db(a):
                 os.replace(id_file + ".tmp", id_file)
             m.nccl_init(_wait_for_file(id_file, float(os.environ.get("PHYLIGN_NCCL_ID_TIMEOUT", 300))), rank, world)
         blocks = qf.block_ranges(a.query_block_bases)
+        # page-locked result buffers pay off when they are reused block after block; a single
+        # (round, block) run fetches once, so plain host memory is cheaper than pinning it
+        m.set_option("pinned_results", int(len(blocks) * max(1, len(plan.rounds)) > 2))
         wstats, gpu_phase_ms, gathered_total, n_writer_blocks = [], np.zeros(3), 0, 0
         direct_merged = direct_arrays = None                   # set when one device merge is already the final answer
         bg = _TPE(max_workers=1)                               # the writer thread (format + gzip + append)
@@ -569,9 +575,10 @@ def cmd_match_db(a):
                              ("GB/s_gathered", f"{round_bytes_by_idx[idx] / max(round_gpu_ms * share, 1e-9) / 1e6:.1f}"),
                              ("rows_read/all", f"{round_bytes_by_idx[idx] / max(1, kmers * rb):.4f}"),
                              ("match_file_bytes", fs.file_bytes.get(idx, 0))])
-                with tm.span("evict_s"):
-                    for idx in loaded:
-                        m.evict(idx)
+                if ri + 1 < len(rounds):                        # (after the last round the process ends anyway)
+                    with tm.span("evict_s"):
+                        for idx in loaded:
+                            m.evict(idx)
         finally:
             if pending_load is not None:
                 try:
@@ -606,6 +613,7 @@ def cmd_match_db(a):
                     for b in batches:
                         _atomic_write(os.path.join(a.bucket_dir, f"{b}____{qfile}.candidates.tsv"),
                                       format_bucket_tsv(buckets.get(brank[b], [])).encode(), gz=False)
+        m.release_at_exit()      # HBM goes back with the process: no cudaFree per index on the way out
         if a.timing_json and (not nccl or rank == 0):
             w = {k: sum(d[k] for d in wstats) for k in (wstats[0] if wstats else {}) if k != "threads"}
             out = {"total_s": tm.total(), "phases_s": {k: round(v, 4) for k, v in tm.t.items()},

@@ -82,7 +82,6 @@ extern "C" int phy_ctx_create(phy_ctx** out, int device, uint64_t hbm_budget) {
     phy_ctx* ctx = new phy_ctx();
     ctx->device = device;
     ctx->n_sm = prop.multiProcessorCount;
-    if (getenv("PHY_KERNEL_PATH")) ctx->kernel_path = atoi(getenv("PHY_KERNEL_PATH"));
     if (getenv("PHY_NO_PRUNE") && atoi(getenv("PHY_NO_PRUNE"))) ctx->prune = false;
     PHY_CUDA(ctx, cudaSetDevice(device));
     size_t fr = 0, tot = 0;
@@ -181,6 +180,21 @@ void phy_pinned_free(void* p) {
         return;
     }
     g_pin_free.insert({it->second, p});
+}
+// result blocks: page-locked from the pool (default) or plain malloc ("pinned_results" 0)
+static void* result_alloc(phy_ctx* ctx, size_t bytes) {
+    return ctx->pinned_results ? phy_pinned_alloc(bytes) : malloc(bytes ? bytes : 1);
+}
+static void result_free(void* p) {
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> lk(g_pin_mu);
+        if (g_pin_cap.find(p) == g_pin_cap.end()) {
+            free(p);
+            return;
+        }
+    }
+    phy_pinned_free(p);
 }
 static bool is_pinned(const void* p) {
     cudaPointerAttributes a;
@@ -625,11 +639,11 @@ extern "C" int phy_results_fetch(phy_ctx* ctx, phy_results** out) {
     r->n_indexes = (uint32_t)n_idx;
     r->n_units = ctx->n_units;
     r->n_hits = ctx->n_hits;
-    r->units = (phy_unit*)phy_pinned_alloc(std::max<uint64_t>(1, r->n_units) * sizeof(phy_unit));
-    r->hits = (phy_hit*)phy_pinned_alloc(std::max<uint64_t>(1, r->n_hits) * sizeof(phy_hit));
+    r->units = (phy_unit*)result_alloc(ctx, std::max<uint64_t>(1, r->n_units) * sizeof(phy_unit));
+    r->hits = (phy_hit*)result_alloc(ctx, std::max<uint64_t>(1, r->n_hits) * sizeof(phy_hit));
     uint32_t* nk = (uint32_t*)malloc((size_t)(ctx->nq + 1) * sizeof(uint32_t));
     if (!r->units || !r->hits || !nk) {
-        phy_pinned_free(r->units); phy_pinned_free(r->hits); free(nk); free(r);
+        result_free(r->units); result_free(r->hits); free(nk); free(r);
         phy_set_error(ctx, "host memory exhausted");
         return PHY_ERR_NOMEM;
     }
@@ -654,8 +668,8 @@ extern "C" int phy_results_fetch(phy_ctx* ctx, phy_results** out) {
 
 extern "C" void phy_results_free(phy_results* r) {
     if (!r) return;
-    phy_pinned_free(r->units);
-    phy_pinned_free(r->hits);
+    result_free(r->units);
+    result_free(r->hits);
     free((void*)r->n_kmers);
     free(r);
 }
@@ -695,8 +709,8 @@ extern "C" int phy_merged_fetch(phy_ctx* ctx, phy_merged** out) {
     m->n_queries = ctx->nq;
     const bool holder = ctx->n_ranks == 1 || ctx->rank == 0;
     const uint64_t n = holder ? ctx->n_final : 0;
-    m->offs = (uint64_t*)phy_pinned_alloc(((size_t)ctx->nq + 1) * sizeof(uint64_t));
-    m->cands = (phy_cand*)phy_pinned_alloc(std::max<uint64_t>(1, n) * sizeof(phy_cand));
+    m->offs = (uint64_t*)result_alloc(ctx, ((size_t)ctx->nq + 1) * sizeof(uint64_t));
+    m->cands = (phy_cand*)result_alloc(ctx, std::max<uint64_t>(1, n) * sizeof(phy_cand));
     if (m->offs) memset(m->offs, 0, ((size_t)ctx->nq + 1) * sizeof(uint64_t));
     if (!m->offs || !m->cands) {
         phy_merged_free(m);
@@ -743,8 +757,8 @@ extern "C" int phy_merge_host(phy_ctx* ctx, uint32_t n_queries, uint32_t top_n, 
 
 extern "C" void phy_merged_free(phy_merged* m) {
     if (!m) return;
-    phy_pinned_free(m->offs);
-    phy_pinned_free(m->cands);
+    result_free(m->offs);
+    result_free(m->cands);
     free(m);
 }
 
@@ -792,7 +806,7 @@ extern "C" int phy_ctx_budget(phy_ctx* ctx, uint64_t* budget, uint64_t* used) {
 extern "C" int phy_ctx_set_option(phy_ctx* ctx, const char* name, int64_t value) {
     if (!ctx || !name) return PHY_ERR_ARG;
     if (!strcmp(name, "prune")) ctx->prune = value != 0;
-    else if (!strcmp(name, "kernel_path") && value >= 1 && value <= 3) ctx->kernel_path = (int)value;
+    else if (!strcmp(name, "pinned_results")) ctx->pinned_results = value != 0;
     else {
         phy_set_error(ctx, "unknown option %s=%lld", name, (long long)value);
         return PHY_ERR_ARG;

@@ -17,14 +17,14 @@
 // Geometry: a row is covered by LPR lanes x 16 B (LPR = 1..32, a power of two chosen from the
 // row stride); a warp holds 32/LPR independent (query,index) units.
 //
-// Three generations of the fused kernel live here (profiles/):
-//   path A  gather_count_fused_kernel   rows -> registers, 8 loads in flight per lane (latency
-//                                       bound, 0.68 of the copy peak; still used for h > 1)
-//   path B  gather_count_bulk_kernel    per-warp smem ring fed by cp.async.bulk + mbarriers
-//   path C  gather_count_ring_kernel    per-warp smem ring fed by lane-private cp.async.cg,
-//                                       persistent warps, 8/10/14 counter planes, exact
-//                                       threshold pruning -- the default (90 % of DRAM peak)
-//   general accum_scores_ring_kernel + select_scores_kernel: K > 16383, D > 4096, phy_scores
+// Kernels (profiles/):
+//   gather_count_ring_kernel   per-warp shared-memory ring fed by lane-private cp.async.cg, persistent
+//                              warps pulling (query, index) units from a global counter, 8/10/14
+//                              counter planes, exact threshold pruning; MULTI = indexes with several
+//                              hash functions (the h rows of a k-mer are AND-ed as they leave the ring)
+//   accum_scores_ring_kernel + select_scores_kernel   the same ring for K > 16383, D > 4096, phy_scores
+// Earlier generations (rows staged in registers; cp.async.bulk + mbarrier ring) were measured in
+// round 1 (profiles/r01_v1_*, r01_v2_*) and removed once the ring kernel covered every index shape.
 #include "phy_internal.cuh"
 
 #include <algorithm>
@@ -34,14 +34,6 @@
 namespace {
 
 constexpr unsigned FULL = 0xFFFFFFFFu;
-
-__device__ __forceinline__ uint4 ldg_row16(const uint8_t* p) {
-    uint4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                 : "l"(p));
-    return v;
-}
 
 // full adder on 32 documents at once: 2 LOP3
 __device__ __forceinline__ void csa(uint32_t& hi, uint32_t& lo, uint32_t a, uint32_t b, uint32_t c) {
@@ -100,81 +92,6 @@ __device__ __forceinline__ uint32_t extract_score(const uint32_t (&pl)[P][4], in
     return s;
 }
 
-// Add `nrows` index rows (one per query k-mer, AND-ed over the hash functions) into the
-// vertical counters of this lane.  colbase = rows + chunk offset + col*16.
-template <int LPR, int P>
-__device__ __forceinline__ void accumulate(uint32_t (&pl)[P][4], const uint8_t* __restrict__ colbase,
-                                           bool lane_on, uint32_t stride, uint64_t sig,
-                                           uint64_t magic, uint32_t num_hashes,
-                                           const uint64_t* __restrict__ hq, uint64_t hstride,
-                                           uint32_t nrows, int lane, unsigned gm) {
-    constexpr int HB = LPR >= 8 ? LPR : 8;  // rows whose hashes are fetched per outer step
-    constexpr int NH = HB / LPR;            // hashes fetched per lane per outer step
-    const int col = lane & (LPR - 1);
-    const int gbase = lane - col;
-    for (uint32_t base = 0; base < nrows; base += HB) {
-        uint32_t myrow[NH];
-#pragma unroll
-        for (int t = 0; t < NH; t++) {
-            uint32_t hidx = base + col + t * LPR;
-            myrow[t] = hidx < nrows ? phy_fastmod(__ldg(hq + hidx), sig, magic) : PHY_ROW_INVALID;
-        }
-#pragma unroll
-        for (int s = 0; s < HB / 8; s++) {
-            if (base + s * 8 >= nrows) break;  // uniform inside the group
-            uint4 v[8];
-#pragma unroll
-            for (int r = 0; r < 8; r++) {
-                const int src = LPR >= 8 ? gbase + s * 8 + r : gbase + (r % LPR);
-                const int slot = LPR >= 8 ? 0 : r / LPR;
-                uint32_t rr = __shfl_sync(gm, myrow[slot], src);
-                if (rr != PHY_ROW_INVALID && lane_on) v[r] = ldg_row16(colbase + (uint64_t)rr * stride);
-                else v[r] = make_uint4(0, 0, 0, 0);
-            }
-            for (uint32_t j = 1; j < num_hashes; j++) {  // AND with the other hash functions' rows
-                uint32_t hidx = base + s * 8 + (LPR >= 8 ? (col & 7) : 0);
-                uint32_t mr[NH];
-#pragma unroll
-                for (int t = 0; t < NH; t++) {
-                    uint32_t hi2 = LPR >= 8 ? hidx : base + col + t * LPR;
-                    mr[t] = hi2 < nrows ? phy_fastmod(__ldg(hq + j * hstride + hi2), sig, magic) : PHY_ROW_INVALID;
-                }
-#pragma unroll
-                for (int r = 0; r < 8; r++) {
-                    const int src = LPR >= 8 ? gbase + r : gbase + (r % LPR);
-                    const int slot = LPR >= 8 ? 0 : r / LPR;
-                    uint32_t rr = __shfl_sync(gm, mr[slot], src);
-                    if (rr != PHY_ROW_INVALID && lane_on) {
-                        uint4 x = ldg_row16(colbase + (uint64_t)rr * stride);
-                        v[r].x &= x.x; v[r].y &= x.y; v[r].z &= x.z; v[r].w &= x.w;
-                    }
-                }
-            }
-#pragma unroll
-            for (int w = 0; w < 4; w++) {
-                auto W = [&](const uint4& q) -> uint32_t {
-                    return w == 0 ? q.x : (w == 1 ? q.y : (w == 2 ? q.z : q.w));
-                };
-                uint32_t twoA, twoB, fourA, fourB, eight;
-                csa(twoA, pl[0][w], pl[0][w], W(v[0]), W(v[1]));
-                csa(twoB, pl[0][w], pl[0][w], W(v[2]), W(v[3]));
-                csa(fourA, pl[1][w], pl[1][w], twoA, twoB);
-                csa(twoA, pl[0][w], pl[0][w], W(v[4]), W(v[5]));
-                csa(twoB, pl[0][w], pl[0][w], W(v[6]), W(v[7]));
-                csa(fourB, pl[1][w], pl[1][w], twoA, twoB);
-                csa(eight, pl[2][w], pl[2][w], fourA, fourB);
-                uint32_t carry = eight;
-#pragma unroll
-                for (int p = 3; p < P; p++) {
-                    uint32_t t = pl[p][w] & carry;
-                    pl[p][w] ^= carry;
-                    carry = t;
-                }
-            }
-        }
-    }
-}
-
 struct GatherArgs {
     const DevIndex* indexes;
     const uint32_t* class_idx;  // index ids handled by this launch (same LPR class)
@@ -197,6 +114,7 @@ struct GatherArgs {
     uint32_t* unit_id;    // [index slot][query] position in units[]
     uint32_t nq;
     uint32_t prune;       // threshold pruning on (ring kernel)
+    uint32_t class_hashes;  // MULTI launches: num_hashes shared by the indexes of the launch
     unsigned long long* idx_bytes;  // [index slot] index-row bytes really gathered (ring kernel)
 };
 
@@ -277,197 +195,22 @@ __device__ __forceinline__ void select_and_emit(const uint32_t (&pl)[P][4], cons
     }
 }
 
-// Fused path A (rows narrower than 128 B, or several hash functions): rows go straight
-// from HBM to registers with 8 independent 128-bit loads in flight per lane.
-// One group of LPR lanes = one (query, index) unit, whole query, whole row.
-template <int LPR>
-__global__ void __launch_bounds__(256, 2) gather_count_fused_kernel(const GatherArgs a) {
-    constexpr int P = PHY_FUSED_PLANES;
-    constexpr int G = 32 / LPR;
-    const int lane = threadIdx.x & 31;
-    const int col = lane & (LPR - 1);
-    const unsigned gm = group_mask<LPR>(lane);
-    const uint64_t warp = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const uint64_t gid = warp * G + (lane / LPR);
-    const uint64_t total = (uint64_t)a.n_class_idx * a.n_q;
-    if (gid >= total) return;  // whole groups leave together
-    const uint32_t ipos = (uint32_t)(gid / a.n_q);
-    const uint32_t q = a.qlist[gid - (uint64_t)ipos * a.n_q];
-    const DevIndex& ix = a.indexes[a.class_idx[ipos]];
-    const uint32_t stride = ix.stride;
-    const uint32_t nrows = a.nk[q];
-
-    uint32_t pl[P][4];
-#pragma unroll
-    for (int p = 0; p < P; p++) pl[p][0] = pl[p][1] = pl[p][2] = pl[p][3] = 0;
-
-    accumulate<LPR, P>(pl, ix.rows + col * 16, (uint32_t)col * 16 < stride, stride, ix.sig, ix.magic,
-                       ix.num_hashes, a.hashes + a.koffs[q], a.total_kmers, nrows, lane, gm);
-    select_and_emit<LPR, P>(pl, a, q, ix.idx_id, ix.n_docs, nrows, lane, gm);
-}
-
-// ---- Fused path B: the HBM-speed kernel for rows of 128-512 B (LPR = 8, 16, 32) ------------
-// The v1 profile (profiles/r01_v1_*) is latency bound: 81% of stall samples wait on the row
-// loads with <= 8 x 512 B in flight per warp.  Here every warp owns a ring of NB batches
-// (8 rows each, 4 KB) in shared memory; rows are fetched with cp.async.bulk (TMA bulk copy,
-// one instruction per row, completion on an mbarrier) NB batches ahead of the carry-save
-// adds, so ~NB*4 KB per warp stay in flight without holding registers.  Warps are
-// persistent and pull (query, index) units from a global counter.
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "W: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@!p bra W;\n\t}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     uint4 v;
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
     return v;
 }
+constexpr int BULK_BATCH_BYTES = 4096;  // one ring batch: 8 rows x (32 lanes x 16 B)
 
-constexpr int BULK_BATCH_BYTES = 4096;  // 8 rows x (32 lanes x 16 B)
-#ifndef PHY_BULK_NB
-#define PHY_BULK_NB 3
-#endif
-#ifndef PHY_BULK_WARPS
-#define PHY_BULK_WARPS 4
-#endif
-constexpr int BULK_NB = PHY_BULK_NB, BULK_WARPS = PHY_BULK_WARPS;
-
-template <int LPR, int NB, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) gather_count_bulk_kernel(const GatherArgs a) {
-    static_assert(LPR >= 8, "bulk path is for row strides >= 128 B");
-    constexpr int P = PHY_FUSED_PLANES;
-    constexpr int G = 32 / LPR;      // units processed side by side by one warp
-    constexpr int BPH = LPR / 8;     // batches per block of LPR hashes
-    constexpr int PITCH = LPR * 16;  // bytes between rows of one group inside a batch
-    extern __shared__ __align__(128) uint8_t smem[];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int col = lane & (LPR - 1), g = lane / LPR;
-    const unsigned gm = group_mask<LPR>(lane);
-    const uint32_t ring = smem_u32(smem) + wid * (NB * BULK_BATCH_BYTES);
-    const uint32_t bars = smem_u32(smem) + WARPS * (NB * BULK_BATCH_BYTES) + wid * (NB * 8);
-    if (lane == 0) {
-#pragma unroll
-        for (int i = 0; i < NB; i++) mbar_init(bars + i * 8, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-    const uint64_t total = (uint64_t)a.n_class_idx * a.n_q;
-    const uint64_t n_wunits = (total + G - 1) / G;
-    uint32_t jg = 0;  // batches issued so far by this warp == slot/phase bookkeeping
-
-    for (;;) {
-        unsigned long long wu = 0;
-        if (lane == 0) wu = atomicAdd(&a.counters[3], 1ULL);
-        wu = __shfl_sync(FULL, wu, 0);
-        if (wu >= n_wunits) break;
-        const uint64_t gid = wu * G + g;
-        const bool live = gid < total;
-        uint32_t q = 0, nrows = 0, stride = 0, n_docs = 0, idx_id = 0;
-        uint64_t sig = 1, magic = 0;
-        const uint8_t* rows = nullptr;
-        const uint64_t* hq = nullptr;
-        if (live) {
-            const uint32_t ipos = (uint32_t)(gid / a.n_q);
-            q = a.qlist[gid - (uint64_t)ipos * a.n_q];
-            const DevIndex& ix = a.indexes[a.class_idx[ipos]];
-            rows = ix.rows; stride = ix.stride; n_docs = ix.n_docs; idx_id = ix.idx_id;
-            sig = ix.sig; magic = ix.magic;
-            nrows = a.nk[q];
-            hq = a.hashes + a.koffs[q];
-        }
-        uint32_t nmax = nrows;
-#pragma unroll
-        for (int o = 16; o >= LPR; o >>= 1) nmax = max(nmax, __shfl_xor_sync(FULL, nmax, o));
-        const uint32_t nb = (nmax + 7) >> 3;  // warp-uniform number of batches
-        const bool lane_on = (uint32_t)col * 16u < stride;
-
-        uint32_t pl[P][4];
-#pragma unroll
-        for (int p = 0; p < P; p++) pl[p][0] = pl[p][1] = pl[p][2] = pl[p][3] = 0;
-
-        uint32_t myrow = PHY_ROW_INVALID;
-        uint64_t hnext = (uint32_t)col < nrows ? __ldg(hq + col) : 0;  // hashes of block 0
-        const uint32_t j0 = jg;
-        auto issue = [&](uint32_t j) {  // j = batch number inside this unit
-            const uint32_t hb = j / BPH, s = j % BPH;
-            if (s == 0) {
-                const uint32_t hidx = hb * LPR + col;
-                myrow = hidx < nrows ? phy_fastmod(hnext, sig, magic) : PHY_ROW_INVALID;
-                const uint32_t hn = hidx + LPR;
-                hnext = hn < nrows ? __ldg(hq + hn) : 0;  // prefetch the next block's hashes
-            }
-            const bool mine = (uint32_t)(col >> 3) == s && myrow != PHY_ROW_INVALID;
-            const unsigned bal = __ballot_sync(FULL, mine);
-            const uint32_t slot = (j0 + j) % NB;
-            const uint32_t bar = bars + slot * 8;
-            if (lane == 0) mbar_expect_tx(bar, (uint32_t)__popc(bal) * stride);
-            if (mine)
-                bulk_g2s(ring + slot * BULK_BATCH_BYTES + (g * 8 + (col & 7)) * PITCH,
-                         rows + (uint64_t)myrow * stride, stride, bar);
-        };
-        const uint32_t npro = nb < (uint32_t)NB ? nb : (uint32_t)NB;
-        for (uint32_t j = 0; j < npro; j++) issue(j);
-        for (uint32_t j = 0; j < nb; j++) {
-            const uint32_t slot = (j0 + j) % NB;
-            mbar_wait(bars + slot * 8, ((j0 + j) / NB) & 1u);
-            const uint32_t src = ring + slot * BULK_BATCH_BYTES + g * 8 * PITCH + col * 16;
-            uint4 v[8];
-#pragma unroll
-            for (int r = 0; r < 8; r++) {
-                if (j * 8 + r < nrows && lane_on) v[r] = lds128(src + r * PITCH);
-                else v[r] = make_uint4(0, 0, 0, 0);
-            }
-#pragma unroll
-            for (int w = 0; w < 4; w++) {
-                auto W = [&](const uint4& x) -> uint32_t {
-                    return w == 0 ? x.x : (w == 1 ? x.y : (w == 2 ? x.z : x.w));
-                };
-                uint32_t twoA, twoB, fourA, fourB, eight;
-                csa(twoA, pl[0][w], pl[0][w], W(v[0]), W(v[1]));
-                csa(twoB, pl[0][w], pl[0][w], W(v[2]), W(v[3]));
-                csa(fourA, pl[1][w], pl[1][w], twoA, twoB);
-                csa(twoA, pl[0][w], pl[0][w], W(v[4]), W(v[5]));
-                csa(twoB, pl[0][w], pl[0][w], W(v[6]), W(v[7]));
-                csa(fourB, pl[1][w], pl[1][w], twoA, twoB);
-                csa(eight, pl[2][w], pl[2][w], fourA, fourB);
-                uint32_t carry = eight;
-#pragma unroll
-                for (int p = 3; p < P; p++) {
-                    uint32_t t = pl[p][w] & carry;
-                    pl[p][w] ^= carry;
-                    carry = t;
-                }
-            }
-            __syncwarp();  // every lane has consumed the slot before it is refilled
-            if (j + NB < nb) issue(j + NB);
-        }
-        jg = j0 + nb;
-        if (live) select_and_emit<LPR, P>(pl, a, q, idx_id, n_docs, nrows, lane, gm);
-        __syncwarp();
-    }
-}
-
-// ---- Fused path C: lane-private cp.async ring (all strides, one hash function) --------------
-// Same ring idea as path B, but every lane copies exactly the 16 B it will read back
-// (cp.async.cg, SASS LDGSTS.BYPASS) and tracks completion with commit/wait groups: no
-// mbarrier, no cross-lane visibility to arrange, 3 instructions per row instead of the
-// 9-instruction UBLKCP issue loop (which makes path B ALU-bound below 256-B rows,
-// profiles/r01_gather_d1000_*).  The carry-save tree is three levels deep here: per 32 rows
-// and 32 documents 4x7 + 2 + 1 full adders and ONE ripple into planes 5.. (2.25 LOP3 per
-// row-word instead of 3.5).
+// ---- the ring: lane-private cp.async staging (all strides) ------------------------------------
+// Every warp owns a ring of NB batches (8 rows each, 4 KB) in shared memory.  Every lane copies
+// exactly the 16 B it will read back (cp.async.cg, SASS LDGSTS.BYPASS) NB batches ahead of the
+// carry-save adds and tracks completion with commit/wait groups: no mbarrier, no cross-lane
+// visibility to arrange, 3 instructions per row (the cp.async.bulk + mbarrier variant of round 1
+// needed a 9-instruction issue loop per row and was ALU-bound below 256-B rows,
+// profiles/r01_gather_d1000_*).  The carry-save tree is three levels deep: per 32 rows and 32
+// documents 4x7 + 2 + 1 full adders and ONE ripple into planes 5.. (2.25 LOP3 per row-word).
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
@@ -684,13 +427,116 @@ __device__ __forceinline__ uint32_t ring_accumulate(uint32_t (&pl)[P][4], uint32
     return min(j * 8u, K);  // rows of this unit that were fetched and counted
 }
 
+// The same for indexes built with several hash functions (num_hashes = h > 1): a k-mer matches a
+// document iff the bit is set in ALL h rows, so the rows of hash function 0..h-1 are
+// AND-ed before they are counted.  The ring streams "virtual batches" jj = j*h + hj (8 k-mers of
+// batch j under hash function hj): same slots, same commit/wait distance; the 8 row pieces of a
+// lane stay in registers across the h virtual batches of one k-mer batch and enter the carry-save
+// tree once, after the last AND.  Hashes are fetched 8 per virtual batch (hq[hj*hstride + i]).
+// Pruning works on the same exact counts as with one hash function.
+template <int LPR, int P, int NB>
+__device__ __forceinline__ uint32_t ring_accumulate_multi(uint32_t (&pl)[P][4], uint32_t ring, const uint8_t* colbase,
+                                                      bool lane_on, uint32_t stride, uint64_t sig, uint64_t magic,
+                                                      const uint64_t* __restrict__ hq, uint64_t hstride, uint32_t h,
+                                                      uint32_t nrows, uint32_t nmax, int lane, uint32_t prune_T,
+                                                      unsigned gm) {
+    constexpr bool FINE = P <= 8;
+    constexpr int NH = LPR >= 8 ? 1 : 8 / LPR;  // hashes per lane per virtual batch (8 rows)
+    const int col = lane & (LPR - 1), gbase = lane - col;
+    uint32_t nb = (nmax + 7) >> 3;              // k-mer batches (warp uniform; shrinks when units die)
+    const uint32_t K = nrows;
+    uint32_t p8[4] = {0, 0, 0, 0}, p16[4] = {0, 0, 0, 0};
+    uint32_t myrow[NH];
+    uint64_t hnext[NH];
+    auto load_hashes = [&](uint32_t jj) {       // hashes of virtual batch jj into hnext
+        const uint32_t j = jj / h, hj = jj - j * h;
+#pragma unroll
+        for (int t = 0; t < NH; t++) {
+            const uint32_t hidx = j * 8 + (uint32_t)col + (uint32_t)t * LPR;
+            const bool mine = (LPR < 8 || col < 8) && hidx < nrows && j < nb;
+            hnext[t] = mine ? __ldg(hq + (uint64_t)hj * hstride + hidx) : 0;
+        }
+    };
+    load_hashes(0);
+    auto issue = [&](uint32_t jj) {
+        const uint32_t j = jj / h;
+        if (j < nb) {
+#pragma unroll
+            for (int t = 0; t < NH; t++) {
+                const uint32_t hidx = j * 8 + (uint32_t)col + (uint32_t)t * LPR;
+                const bool mine = (LPR < 8 || col < 8) && hidx < nrows;
+                myrow[t] = mine ? phy_fastmod(hnext[t], sig, magic) : PHY_ROW_INVALID;
+            }
+            load_hashes(jj + 1);
+            const uint32_t dst = ring + (jj % NB) * BULK_BATCH_BYTES;
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                const int src = LPR >= 8 ? gbase + r : gbase + (r % LPR);
+                const int slot = LPR >= 8 ? 0 : r / LPR;
+                const uint32_t rr = __shfl_sync(FULL, myrow[slot], src);
+                if (rr != PHY_ROW_INVALID && j * 8 + r < nrows && lane_on)
+                    cp_async16(dst + r * 512, colbase + (uint64_t)rr * stride);
+            }
+        }
+        cp_async_commit();
+    };
+#pragma unroll 1
+    for (uint32_t jj = 0; jj < (uint32_t)NB; jj++) issue(jj);
+    const bool prune_any = __any_sync(FULL, prune_T != 0);
+    uint4 v[8];
+    uint32_t j = 0, hj = 0, jj = 0;
+#pragma unroll 1
+    for (; j < nb; jj++) {
+        cp_async_wait<NB - 1>();
+        const uint32_t src = ring + (jj % NB) * BULK_BATCH_BYTES;
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            uint4 x = make_uint4(0, 0, 0, 0);
+            if (j * 8 + r < nrows && lane_on) x = lds128(src + r * 512);
+            if (hj == 0) v[r] = x;
+            else { v[r].x &= x.x; v[r].y &= x.y; v[r].z &= x.z; v[r].w &= x.w; }
+        }
+        if (++hj == h) {                        // all hash functions of k-mer batch j are in: count it
+            hj = 0;
+            if constexpr (FINE) csa_batch2<P>(pl, v, j, p8);
+            else csa_batch3<P>(pl, v, j, p8, p16);
+            if (prune_any && ((j + 1) & (FINE ? 1u : 3u)) == 0) {
+                const uint32_t x = min((j + 1) * 8u, nrows);
+                bool alive = lane_on;
+                if (lane_on && prune_T != 0 && prune_T + x > K) {
+                    const uint32_t need = prune_T + x - K;
+                    uint32_t any = 0;
+#pragma unroll
+                    for (int w = 0; w < 4; w++) any |= ge_mask<P>(pl, w, need);
+                    alive = any != 0;
+                    lane_on = alive;
+                }
+                const unsigned live = __ballot_sync(FULL, alive && x < nrows);
+                if ((live & gm) == 0 && x < nrows) nrows = x;
+                if (live != FULL) {
+                    uint32_t m = (nrows + 7) >> 3;
+#pragma unroll
+                    for (int o = 16; o >= LPR; o >>= 1) m = max(m, __shfl_xor_sync(FULL, m, o));
+                    nb = max(m, j + 1);
+                }
+            }
+            j++;
+        }
+        issue(jj + NB);
+    }
+    cp_async_wait<0>();
+    if constexpr (FINE) csa_flush2<P>(pl, j, p8);
+    else csa_flush3<P>(pl, j, p8, p16);
+    return min(j * 8u, K);
+}
+
 #ifndef PHY_RING_MINBLOCKS
 #define PHY_RING_MINBLOCKS 1
 #endif
 #ifndef PHY_RING_MINBLOCKS_SHORT
 #define PHY_RING_MINBLOCKS_SHORT 1
 #endif
-template <int LPR, int P, int NB, int WARPS>
+template <int LPR, int P, int NB, int WARPS, bool MULTI>
 __global__ void __launch_bounds__(WARPS * 32, (P <= 8 ? PHY_RING_MINBLOCKS_SHORT : PHY_RING_MINBLOCKS))
 gather_count_ring_kernel(const GatherArgs a) {
     constexpr int G = 32 / LPR;
@@ -732,8 +578,15 @@ gather_count_ring_kernel(const GatherArgs a) {
 #pragma unroll
         for (int p = 0; p < P; p++) pl[p][0] = pl[p][1] = pl[p][2] = pl[p][3] = 0;
         const uint32_t prune_T = (a.prune && live) ? a.T[q] : 0u;
-        const uint32_t done = ring_accumulate<LPR, P, NB>(pl, ring, colbase, (uint32_t)col * 16u < stride, stride,
-                                                          sig, magic, hq, nrows, nmax, lane, prune_T, gm);
+        uint32_t done;
+        if constexpr (MULTI) {
+            const uint32_t h = a.class_hashes;  // a launch holds indexes with the same number of hash functions
+            done = ring_accumulate_multi<LPR, P, NB>(pl, ring, colbase, (uint32_t)col * 16u < stride, stride, sig, magic,
+                                                     hq, a.total_kmers, h, nrows, nmax, lane, prune_T, gm) * h;
+        } else {
+            done = ring_accumulate<LPR, P, NB>(pl, ring, colbase, (uint32_t)col * 16u < stride, stride, sig, magic, hq,
+                                               nrows, nmax, lane, prune_T, gm);
+        }
         if (live && col == 0)  // bytes of index rows this unit really gathered (pruning makes it < K rows)
             atomicAdd(&a.idx_bytes[idx_id], (unsigned long long)done * ((n_docs + 7u) >> 3));
         if (live) select_and_emit<LPR, P>(pl, a, q, idx_id, n_docs, nrows, lane, gm);
@@ -745,11 +598,11 @@ gather_count_ring_kernel(const GatherArgs a) {
 // one 512-B column chunk, flushed into a dense uint32 score row with atomics.  Chunks hold up
 // to 2^14-1 k-mers (14 planes).  For K > PHY_LONG_KMAX, rows wider than 512 B (D > 4096), phy_scores().
 constexpr int PHY_GENERAL_PLANES = 14;
-template <int LPR, int NB, int WARPS>
+template <int LPR, int NB, int WARPS, bool MULTI>
 __global__ void __launch_bounds__(WARPS * 32) accum_scores_ring_kernel(
     const DevIndex* __restrict__ ixp, const SlowItem* __restrict__ items, uint32_t n_items, uint32_t n_chunks,
-    const uint64_t* __restrict__ koffs, const uint64_t* __restrict__ hashes, uint32_t* __restrict__ scores,
-    unsigned long long* __restrict__ counter) {
+    const uint64_t* __restrict__ koffs, const uint64_t* __restrict__ hashes, uint64_t hstride,
+    uint32_t* __restrict__ scores, unsigned long long* __restrict__ counter) {
     constexpr int P = PHY_GENERAL_PLANES;
     constexpr int G = 32 / LPR;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -781,9 +634,13 @@ __global__ void __launch_bounds__(WARPS * 32) accum_scores_ring_kernel(
         uint32_t pl[P][4];
 #pragma unroll
         for (int p = 0; p < P; p++) pl[p][0] = pl[p][1] = pl[p][2] = pl[p][3] = 0;
-        ring_accumulate<LPR, P, NB>(pl, ring, ix.rows + byte0, live && byte0 < stride, stride, ix.sig, ix.magic,
-                                    hashes + (live ? koffs[it.query] + it.k0 : 0), nrows, nmax, lane, 0u,
-                                    group_mask<LPR>(lane));
+        const uint64_t* hq = hashes + (live ? koffs[it.query] + it.k0 : 0);
+        if constexpr (MULTI)
+            ring_accumulate_multi<LPR, P, NB>(pl, ring, ix.rows + byte0, live && byte0 < stride, stride, ix.sig, ix.magic,
+                                              hq, hstride, ix.num_hashes, nrows, nmax, lane, 0u, group_mask<LPR>(lane));
+        else
+            ring_accumulate<LPR, P, NB>(pl, ring, ix.rows + byte0, live && byte0 < stride, stride, ix.sig, ix.magic, hq,
+                                        nrows, nmax, lane, 0u, group_mask<LPR>(lane));
         if (live) {
             uint32_t* row = scores + (uint64_t)it.slot * n_docs;
 #pragma unroll
@@ -800,48 +657,6 @@ __global__ void __launch_bounds__(WARPS * 32) accum_scores_ring_kernel(
             }
         }
         __syncwarp();
-    }
-}
-
-// General path: k-mers [k0,k1) of a query against ONE index and one 512-B column chunk,
-// flushed into a dense uint32 score row.  Used for queries with K > PHY_FUSED_KMAX, for
-// rows wider than 512 B (D > 4096) and by phy_scores().
-template <int LPR>
-__global__ void __launch_bounds__(256, 2) accum_scores_kernel(
-    const DevIndex* __restrict__ ixp, const SlowItem* __restrict__ items, uint32_t n_items,
-    uint32_t n_chunks, const uint64_t* __restrict__ koffs, const uint64_t* __restrict__ hashes,
-    uint64_t total_kmers, uint32_t* __restrict__ scores) {
-    constexpr int P = PHY_FUSED_PLANES;
-    constexpr int G = 32 / LPR;
-    const int lane = threadIdx.x & 31;
-    const int col = lane & (LPR - 1);
-    const unsigned gm = group_mask<LPR>(lane);
-    const uint64_t warp = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const uint64_t gid = warp * G + (lane / LPR);
-    if (gid >= (uint64_t)n_items * n_chunks) return;
-    const SlowItem it = items[gid / n_chunks];
-    const uint32_t chunk = (uint32_t)(gid % n_chunks);
-    const DevIndex& ix = *ixp;
-    const uint32_t stride = ix.stride, n_docs = ix.n_docs;
-    const uint32_t byte0 = chunk * PHY_CHUNK_BYTES + (uint32_t)col * 16u;
-
-    uint32_t pl[P][4];
-#pragma unroll
-    for (int p = 0; p < P; p++) pl[p][0] = pl[p][1] = pl[p][2] = pl[p][3] = 0;
-    accumulate<LPR, P>(pl, ix.rows + byte0, byte0 < stride, stride, ix.sig, ix.magic, ix.num_hashes,
-                       hashes + koffs[it.query] + it.k0, total_kmers, it.k1 - it.k0, lane, gm);
-    uint32_t* row = scores + (uint64_t)it.slot * n_docs;
-#pragma unroll
-    for (int w = 0; w < 4; w++) {
-        uint32_t any = 0;
-#pragma unroll
-        for (int p = 0; p < P; p++) any |= pl[p][w];
-        const uint32_t d0 = byte0 * 8u + w * 32u;
-        while (any) {
-            int b = __ffs(any) - 1;
-            any &= any - 1;
-            if (d0 + b < n_docs) atomicAdd(&row[d0 + b], extract_score<P>(pl, w, b));
-        }
     }
 }
 
@@ -929,126 +744,79 @@ int lpr_for_stride(uint32_t stride) {
     return lpr;
 }
 
-template <int LPR>
-void launch_fused(const GatherArgs& a, cudaStream_t st) {
-    constexpr int G = 32 / LPR;
-    uint64_t groups = (uint64_t)a.n_class_idx * a.n_q;
-    uint64_t warps = (groups + G - 1) / G;
-    unsigned blocks = (unsigned)((warps + 7) / 8);
-    if (blocks) gather_count_fused_kernel<LPR><<<blocks, 256, 0, st>>>(a);
-}
-
-template <int LPR, int NB, int WARPS>
-int launch_bulk(const GatherArgs& a, cudaStream_t st, int n_sm) {
-    constexpr int SMEM = WARPS * NB * BULK_BATCH_BYTES + WARPS * NB * 8;
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(gather_count_bulk_kernel<LPR, NB, WARPS>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) return -1;
-        configured = true;
-    }
-    int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gather_count_bulk_kernel<LPR, NB, WARPS>,
-                                                      WARPS * 32, SMEM) != cudaSuccess || per_sm < 1) return -1;
-    constexpr int G = 32 / LPR;
-    uint64_t wunits = ((uint64_t)a.n_class_idx * a.n_q + G - 1) / G;
-    uint64_t blocks = std::min<uint64_t>((wunits + WARPS - 1) / WARPS, (uint64_t)n_sm * per_sm);
-    if (blocks) gather_count_bulk_kernel<LPR, NB, WARPS><<<(unsigned)blocks, WARPS * 32, SMEM, st>>>(a);
-    return 0;
-}
-
-template <int LPR, int P, int NB, int WARPS>
+template <int LPR, int P, int NB, int WARPS, bool MULTI>
 int launch_ring(const GatherArgs& a, cudaStream_t st, int n_sm) {
     constexpr int SMEM = WARPS * NB * BULK_BATCH_BYTES;
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(gather_count_ring_kernel<LPR, P, NB, WARPS>,
+        if (cudaFuncSetAttribute(gather_count_ring_kernel<LPR, P, NB, WARPS, MULTI>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) return -1;
         configured = true;
     }
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gather_count_ring_kernel<LPR, P, NB, WARPS>,
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gather_count_ring_kernel<LPR, P, NB, WARPS, MULTI>,
                                                       WARPS * 32, SMEM) != cudaSuccess || per_sm < 1) return -1;
     constexpr int G = 32 / LPR;
     uint64_t wunits = ((uint64_t)a.n_class_idx * a.n_q + G - 1) / G;
     uint64_t blocks = std::min<uint64_t>((wunits + WARPS - 1) / WARPS, (uint64_t)n_sm * per_sm);
-    if (blocks) gather_count_ring_kernel<LPR, P, NB, WARPS><<<(unsigned)blocks, WARPS * 32, SMEM, st>>>(a);
+    if (blocks) gather_count_ring_kernel<LPR, P, NB, WARPS, MULTI><<<(unsigned)blocks, WARPS * 32, SMEM, st>>>(a);
     return 0;
 }
-template <int P>
+template <int P, bool MULTI>
 int dispatch_ring(int c, const GatherArgs& a, cudaStream_t st, int n_sm) {
     // short-read class (8 planes): units of <= 255 rows die early under pruning, a 2-deep ring wastes
     // one batch less when they do (measured 7 % faster on 150-bp reads than the 3-deep ring)
     constexpr int NB = P <= 8 ? PHY_RING_NB_SHORT : RING_NB;
     switch (c) {
-        case 0: return launch_ring<1, P, NB, RING_WARPS>(a, st, n_sm);
-        case 1: return launch_ring<2, P, NB, RING_WARPS>(a, st, n_sm);
-        case 2: return launch_ring<4, P, NB, RING_WARPS>(a, st, n_sm);
-        case 3: return launch_ring<8, P, NB, RING_WARPS>(a, st, n_sm);
-        case 4: return launch_ring<16, P, NB, RING_WARPS>(a, st, n_sm);
-        default: return launch_ring<32, P, NB, RING_WARPS>(a, st, n_sm);
+        case 0: return launch_ring<1, P, NB, RING_WARPS, MULTI>(a, st, n_sm);
+        case 1: return launch_ring<2, P, NB, RING_WARPS, MULTI>(a, st, n_sm);
+        case 2: return launch_ring<4, P, NB, RING_WARPS, MULTI>(a, st, n_sm);
+        case 3: return launch_ring<8, P, NB, RING_WARPS, MULTI>(a, st, n_sm);
+        case 4: return launch_ring<16, P, NB, RING_WARPS, MULTI>(a, st, n_sm);
+        default: return launch_ring<32, P, NB, RING_WARPS, MULTI>(a, st, n_sm);
     }
 }
+template <bool MULTI>
+int dispatch_ring_planes(int pass, int c, const GatherArgs& a, cudaStream_t st, int n_sm) {
+    return pass == 0 ? dispatch_ring<10, MULTI>(c, a, st, n_sm)
+         : pass == 1 ? dispatch_ring<8, MULTI>(c, a, st, n_sm)
+                     : dispatch_ring<14, MULTI>(c, a, st, n_sm);
+}
 
-template <int LPR>
+template <int LPR, bool MULTI>
 int launch_accum_ring(const DevIndex* ixp, const SlowItem* items, uint32_t n_items, uint32_t n_chunks,
-                      const uint64_t* koffs, const uint64_t* hashes, uint32_t* scores,
+                      const uint64_t* koffs, const uint64_t* hashes, uint64_t hstride, uint32_t* scores,
                       unsigned long long* counter, cudaStream_t st, int n_sm) {
     constexpr int NB = RING_NB, WARPS = RING_WARPS;
     constexpr int SMEM = WARPS * NB * BULK_BATCH_BYTES;
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(accum_scores_ring_kernel<LPR, NB, WARPS>,
+        if (cudaFuncSetAttribute(accum_scores_ring_kernel<LPR, NB, WARPS, MULTI>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) return -1;
         configured = true;
     }
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, accum_scores_ring_kernel<LPR, NB, WARPS>, WARPS * 32,
-                                                      SMEM) != cudaSuccess || per_sm < 1) return -1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, accum_scores_ring_kernel<LPR, NB, WARPS, MULTI>,
+                                                      WARPS * 32, SMEM) != cudaSuccess || per_sm < 1) return -1;
     constexpr int G = 32 / LPR;
     uint64_t wunits = ((uint64_t)n_items * n_chunks + G - 1) / G;
     uint64_t blocks = std::min<uint64_t>((wunits + WARPS - 1) / WARPS, (uint64_t)n_sm * per_sm);
     if (blocks)
-        accum_scores_ring_kernel<LPR, NB, WARPS><<<(unsigned)blocks, WARPS * 32, SMEM, st>>>(
-            ixp, items, n_items, n_chunks, koffs, hashes, scores, counter);
+        accum_scores_ring_kernel<LPR, NB, WARPS, MULTI><<<(unsigned)blocks, WARPS * 32, SMEM, st>>>(
+            ixp, items, n_items, n_chunks, koffs, hashes, hstride, scores, counter);
     return 0;
 }
+template <bool MULTI>
 int dispatch_accum_ring(int lpr, const DevIndex* ixp, const SlowItem* items, uint32_t n_items, uint32_t n_chunks,
-                        const uint64_t* koffs, const uint64_t* hashes, uint32_t* scores,
+                        const uint64_t* koffs, const uint64_t* hashes, uint64_t hstride, uint32_t* scores,
                         unsigned long long* counter, cudaStream_t st, int n_sm) {
     switch (lpr) {
-        case 1: return launch_accum_ring<1>(ixp, items, n_items, n_chunks, koffs, hashes, scores, counter, st, n_sm);
-        case 2: return launch_accum_ring<2>(ixp, items, n_items, n_chunks, koffs, hashes, scores, counter, st, n_sm);
-        case 4: return launch_accum_ring<4>(ixp, items, n_items, n_chunks, koffs, hashes, scores, counter, st, n_sm);
-        case 8: return launch_accum_ring<8>(ixp, items, n_items, n_chunks, koffs, hashes, scores, counter, st, n_sm);
-        case 16: return launch_accum_ring<16>(ixp, items, n_items, n_chunks, koffs, hashes, scores, counter, st, n_sm);
-        default: return launch_accum_ring<32>(ixp, items, n_items, n_chunks, koffs, hashes, scores, counter, st, n_sm);
-    }
-}
-
-template <int LPR>
-void launch_accum(const DevIndex* ixp, const SlowItem* items, uint32_t n_items, uint32_t n_chunks,
-                  const uint64_t* koffs, const uint64_t* hashes, uint64_t total_kmers,
-                  uint32_t* scores, cudaStream_t st) {
-    constexpr int G = 32 / LPR;
-    uint64_t groups = (uint64_t)n_items * n_chunks;
-    uint64_t warps = (groups + G - 1) / G;
-    unsigned blocks = (unsigned)((warps + 7) / 8);
-    if (blocks)
-        accum_scores_kernel<LPR><<<blocks, 256, 0, st>>>(ixp, items, n_items, n_chunks, koffs, hashes,
-                                                        total_kmers, scores);
-}
-
-void dispatch_accum(int lpr, const DevIndex* ixp, const SlowItem* items, uint32_t n_items,
-                    uint32_t n_chunks, const uint64_t* koffs, const uint64_t* hashes,
-                    uint64_t total_kmers, uint32_t* scores, cudaStream_t st) {
-    switch (lpr) {
-        case 1: launch_accum<1>(ixp, items, n_items, n_chunks, koffs, hashes, total_kmers, scores, st); break;
-        case 2: launch_accum<2>(ixp, items, n_items, n_chunks, koffs, hashes, total_kmers, scores, st); break;
-        case 4: launch_accum<4>(ixp, items, n_items, n_chunks, koffs, hashes, total_kmers, scores, st); break;
-        case 8: launch_accum<8>(ixp, items, n_items, n_chunks, koffs, hashes, total_kmers, scores, st); break;
-        case 16: launch_accum<16>(ixp, items, n_items, n_chunks, koffs, hashes, total_kmers, scores, st); break;
-        default: launch_accum<32>(ixp, items, n_items, n_chunks, koffs, hashes, total_kmers, scores, st); break;
+        case 1: return launch_accum_ring<1, MULTI>(ixp, items, n_items, n_chunks, koffs, hashes, hstride, scores, counter, st, n_sm);
+        case 2: return launch_accum_ring<2, MULTI>(ixp, items, n_items, n_chunks, koffs, hashes, hstride, scores, counter, st, n_sm);
+        case 4: return launch_accum_ring<4, MULTI>(ixp, items, n_items, n_chunks, koffs, hashes, hstride, scores, counter, st, n_sm);
+        case 8: return launch_accum_ring<8, MULTI>(ixp, items, n_items, n_chunks, koffs, hashes, hstride, scores, counter, st, n_sm);
+        case 16: return launch_accum_ring<16, MULTI>(ixp, items, n_items, n_chunks, koffs, hashes, hstride, scores, counter, st, n_sm);
+        default: return launch_accum_ring<32, MULTI>(ixp, items, n_items, n_chunks, koffs, hashes, hstride, scores, counter, st, n_sm);
     }
 }
 
@@ -1069,28 +837,26 @@ int phy_lpr_for_stride(uint32_t stride) { return lpr_for_stride(stride); }
 // Run the general path for `slots` (query ids) against index ix; scores into d_scores.
 static int run_general(phy_ctx* ctx, const HostIndex& ix, int ipos, const std::vector<uint32_t>& slot_queries,
                        uint32_t* d_scores_out) {
-    const bool use_ring = ix.d.num_hashes == 1 && ctx->kernel_path != 1;
-    const uint32_t cmax = use_ring ? PHY_LONG_KMAX : PHY_FUSED_KMAX;
     std::vector<SlowItem> items;
     for (uint32_t s = 0; s < slot_queries.size(); s++)
-        push_items(items, s, slot_queries[s], ctx->h_nk[slot_queries[s]], cmax);
+        push_items(items, s, slot_queries[s], ctx->h_nk[slot_queries[s]], PHY_LONG_KMAX);
     const size_t n_sc = slot_queries.size() * (size_t)ix.d.n_docs;
     PHY_CUDA(ctx, cudaMemsetAsync(d_scores_out, 0, n_sc * sizeof(uint32_t), ctx->stream));
     if (items.empty()) return PHY_OK;
     PHY_TRY(phy_ensure(ctx, ctx->d_items, items.size()));
     PHY_TRY(phy_h2d(ctx, ctx->d_items.p, items.data(), items.size() * sizeof(SlowItem)));
     const uint32_t n_chunks = (ix.d.stride + PHY_CHUNK_BYTES - 1) / PHY_CHUNK_BYTES;
-    if (use_ring) {
-        PHY_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p + 4, 0, sizeof(unsigned long long), ctx->stream));
-        if (dispatch_accum_ring(ix.lpr, ctx->d_indexes.p + ipos, ctx->d_items.p, (uint32_t)items.size(), n_chunks,
-                                ctx->d_koffs.p, ctx->d_hashes.p, d_scores_out, ctx->d_counters.p + 4, ctx->stream,
-                                ctx->n_sm) != 0) {
-            phy_set_error(ctx, "cannot configure the ring score kernel: %s", cudaGetErrorString(cudaGetLastError()));
-            return PHY_ERR_CUDA;
-        }
-    } else {
-        dispatch_accum(ix.lpr, ctx->d_indexes.p + ipos, ctx->d_items.p, (uint32_t)items.size(), n_chunks,
-                       ctx->d_koffs.p, ctx->d_hashes.p, ctx->total_kmers, d_scores_out, ctx->stream);
+    PHY_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p + 4, 0, sizeof(unsigned long long), ctx->stream));
+    const int rc = ix.d.num_hashes > 1
+        ? dispatch_accum_ring<true>(ix.lpr, ctx->d_indexes.p + ipos, ctx->d_items.p, (uint32_t)items.size(), n_chunks,
+                                    ctx->d_koffs.p, ctx->d_hashes.p, ctx->total_kmers, d_scores_out,
+                                    ctx->d_counters.p + 4, ctx->stream, ctx->n_sm)
+        : dispatch_accum_ring<false>(ix.lpr, ctx->d_indexes.p + ipos, ctx->d_items.p, (uint32_t)items.size(), n_chunks,
+                                     ctx->d_koffs.p, ctx->d_hashes.p, ctx->total_kmers, d_scores_out,
+                                     ctx->d_counters.p + 4, ctx->stream, ctx->n_sm);
+    if (rc != 0) {
+        phy_set_error(ctx, "cannot configure the ring score kernel: %s", cudaGetErrorString(cudaGetLastError()));
+        return PHY_ERR_CUDA;
     }
     ctx->launches++;
     PHY_CUDA(ctx, cudaGetLastError());
@@ -1108,9 +874,7 @@ int phy_launch_scores(phy_ctx* ctx, int idx_id, uint32_t* d_out_scores) {
 int phy_launch_gather(phy_ctx* ctx, const phy_match_params* p) {
     // per-query minimum score T (host double arithmetic, identical to the oracle / cobs) and the
     // query classes by k-mer count: <= 255 (8 counter planes), <= 1023 (10), <= 16383 (14) are fused
-    // in the ring kernel; longer ones go through the chunked dense-score path.  Indexes the ring
-    // kernel cannot take (several hash functions, or a forced legacy kernel path) fuse K <= 1023
-    // with 10 planes and send everything longer through the general path.
+    // in the ring kernel; longer ones go through the chunked dense-score path.
     std::vector<uint32_t> T(ctx->nq), shortq, fastq, midq, slowq;
     for (uint32_t q = 0; q < ctx->nq; q++) {
         double x = p->threshold * (double)ctx->h_nk[q];
@@ -1152,22 +916,30 @@ int phy_launch_gather(phy_ctx* ctx, const phy_match_params* p) {
     PHY_TRY(phy_ensure(ctx, ctx->d_qcount, ctx->nq + 1));
     PHY_TRY(phy_ensure(ctx, ctx->d_counters, 8));
 
-    // index classes
-    // cls[0..5]: ring-kernel indexes by lanes-per-row 1,2,4,8,16,32; cls[6..11]: the same for
-    // indexes on a legacy kernel; rows wider than 512 B take the general path for every query
-    auto ring_ok = [&](const HostIndex& ix) { return ix.d.num_hashes == 1 && ctx->kernel_path == 3; };
-    std::vector<uint32_t> cls[12];
+    // index classes: one launch per (lanes-per-row class, number of hash functions, query class);
+    // rows wider than 512 B take the general path for every query
+    struct IdxClass { int c; uint32_t h; std::vector<uint32_t> ids; size_t off; };
+    std::vector<IdxClass> classes;
     for (size_t i = 0; i < ctx->idx.size(); i++) {
         const HostIndex& ix = ctx->idx[i];
         if (!ix.alive || !ix.committed || !ix.active) continue;
         if (ix.d.stride > PHY_CHUNK_BYTES) continue;
         int c = 0;
         while ((1 << c) < ix.lpr) c++;
-        cls[ring_ok(ix) ? c : c + 6].push_back((uint32_t)i);
+        IdxClass* k = nullptr;
+        for (auto& x : classes)
+            if (x.c == c && x.h == ix.d.num_hashes) k = &x;
+        if (!k) {
+            classes.push_back(IdxClass{c, ix.d.num_hashes, {}, 0});
+            k = &classes.back();
+        }
+        k->ids.push_back((uint32_t)i);
     }
+    std::sort(classes.begin(), classes.end(), [](const IdxClass& x, const IdxClass& y) {
+        return x.h != y.h ? x.h < y.h : x.c < y.c;
+    });
     std::vector<uint32_t> class_flat;
-    size_t class_off[12];
-    for (int c = 0; c < 12; c++) { class_off[c] = class_flat.size(); class_flat.insert(class_flat.end(), cls[c].begin(), cls[c].end()); }
+    for (auto& k : classes) { k.off = class_flat.size(); class_flat.insert(class_flat.end(), k.ids.begin(), k.ids.end()); }
     uint32_t* d_class = nullptr;
     if (!class_flat.empty()) {
         PHY_TRY(phy_ensure(ctx, ctx->d_class, class_flat.size()));
@@ -1217,18 +989,17 @@ int phy_launch_gather(phy_ctx* ctx, const phy_match_params* p) {
             a.unit_id = ctx->d_unit_id.p;
         }
         if (!fastq.empty()) {
-            for (int c = 0; c < 6; c++) {  // path C: lane-private cp.async ring, persistent warps
-                if (cls[c].empty()) continue;
-                a.class_idx = d_class + class_off[c];
-                a.n_class_idx = (uint32_t)cls[c].size();
+            for (const IdxClass& k : classes) {  // persistent warps pull (query, index) units of the class
+                a.class_idx = d_class + k.off;
+                a.n_class_idx = (uint32_t)k.ids.size();
+                a.class_hashes = k.h;
                 for (int pass = 0; pass < 3; pass++) {   // 10-plane, 8-plane, 14-plane query classes
                     a.qlist = ctx->d_qlist.p + (pass == 0 ? 0 : pass == 1 ? n_fast10 : n_le1023);
                     a.n_q = pass == 0 ? n_fast10 : pass == 1 ? n_fast8 : n_fast14;
                     if (a.n_q == 0) continue;
                     PHY_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p + 3, 0, sizeof(unsigned long long), ctx->stream));
-                    int rc = pass == 0 ? dispatch_ring<10>(c, a, ctx->stream, ctx->n_sm)
-                           : pass == 1 ? dispatch_ring<8>(c, a, ctx->stream, ctx->n_sm)
-                                       : dispatch_ring<14>(c, a, ctx->stream, ctx->n_sm);
+                    const int rc = k.h > 1 ? dispatch_ring_planes<true>(pass, k.c, a, ctx->stream, ctx->n_sm)
+                                           : dispatch_ring_planes<false>(pass, k.c, a, ctx->stream, ctx->n_sm);
                     if (rc != 0) {
                         phy_set_error(ctx, "cannot configure the ring gather kernel: %s",
                                       cudaGetErrorString(cudaGetLastError()));
@@ -1238,36 +1009,6 @@ int phy_launch_gather(phy_ctx* ctx, const phy_match_params* p) {
                     PHY_CUDA(ctx, cudaGetLastError());
                 }
             }
-            a.qlist = ctx->d_qlist.p;
-            a.n_q = n_le1023;              // legacy kernels hold 10 planes: every query with K <= 1023
-            for (int c = 0; c < 6 && a.n_q; c++) {
-                if (cls[c + 6].empty()) continue;
-                a.class_idx = d_class + class_off[c + 6];
-                a.n_class_idx = (uint32_t)cls[c + 6].size();
-                bool multi_hash = false;
-                for (uint32_t i : cls[c + 6]) multi_hash |= ctx->idx[i].d.num_hashes > 1;
-                const bool bulk = c >= 3 && !multi_hash && ctx->kernel_path == 2;
-                if (bulk) {  // path B: cp.async.bulk ring
-                    PHY_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p + 3, 0, sizeof(unsigned long long), ctx->stream));
-                    int rc = c == 3 ? launch_bulk<8, BULK_NB, BULK_WARPS>(a, ctx->stream, ctx->n_sm)
-                           : c == 4 ? launch_bulk<16, BULK_NB, BULK_WARPS>(a, ctx->stream, ctx->n_sm)
-                                    : launch_bulk<32, BULK_NB, BULK_WARPS>(a, ctx->stream, ctx->n_sm);
-                    if (rc != 0) {
-                        phy_set_error(ctx, "cannot configure the bulk gather kernel: %s",
-                                      cudaGetErrorString(cudaGetLastError()));
-                        return PHY_ERR_CUDA;
-                    }
-                } else switch (c) {  // path A: rows straight to registers (also: several hash functions)
-                    case 0: launch_fused<1>(a, ctx->stream); break;
-                    case 1: launch_fused<2>(a, ctx->stream); break;
-                    case 2: launch_fused<4>(a, ctx->stream); break;
-                    case 3: launch_fused<8>(a, ctx->stream); break;
-                    case 4: launch_fused<16>(a, ctx->stream); break;
-                    default: launch_fused<32>(a, ctx->stream); break;
-                }
-                ctx->launches++;
-                PHY_CUDA(ctx, cudaGetLastError());
-            }
         }
         // general path: long queries against every index; every query against wide indexes
         for (size_t i = 0; i < ctx->idx.size(); i++) {
@@ -1276,7 +1017,6 @@ int phy_launch_gather(phy_ctx* ctx, const phy_match_params* p) {
             const bool is_wide = ix.d.stride > PHY_CHUNK_BYTES;
             std::vector<uint32_t> qs = slowq;
             if (is_wide) qs.insert(qs.end(), fastq.begin(), fastq.end());
-            else if (!ring_ok(ix)) qs.insert(qs.end(), midq.begin(), midq.end());  // K > 1023 on a legacy kernel
             if (qs.empty()) continue;
             // bounded scratch: process slots in groups of <= 256 MB of scores
             size_t per = std::max<size_t>(1, (size_t)(64u << 20) / std::max<uint32_t>(1, ix.d.n_docs));

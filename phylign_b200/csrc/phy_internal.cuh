@@ -58,7 +58,7 @@ struct HostIndex {
 struct phy_ctx {
     int device = 0, n_sm = 148;
     bool prune = true;    // PHY_NO_PRUNE=1 switches the exact threshold pruning of the ring kernel off
-    int kernel_path = 3;  // PHY_KERNEL_PATH: 1 = register-staged (A), 2 = bulk-copy ring (B), 3 = cp.async ring (C)
+    bool pinned_results = true;  // phy_results / phy_merged blocks from the page-locked pool
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_ph[4] = {nullptr, nullptr, nullptr, nullptr};
     uint64_t budget = 0, used = 0;

@@ -76,9 +76,9 @@ extern "C" int phy_fasta_read(const char* path, phy_fasta** out) {
     }
     phy_fasta* f = (phy_fasta*)calloc(1, sizeof(phy_fasta));
     if (!f) return PHY_ERR_NOMEM;
-    f->seqs = (char*)phy_pinned_alloc(len + 64);
-    f->seqs_pinned = f->seqs != nullptr;
-    if (!f->seqs) f->seqs = (char*)malloc(len + 64);
+    // plain host memory: page-locking ~100 MB costs more than the one staged upload it would save
+    f->seqs = (char*)malloc(len + 64);
+    f->seqs_pinned = 0;
     f->soffs = (uint64_t*)malloc((n_rec + 1) * sizeof(uint64_t));
     f->headers = (char*)malloc(len + 1);
     f->hoffs = (uint64_t*)malloc((n_rec + 1) * sizeof(uint64_t));

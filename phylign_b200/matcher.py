@@ -140,8 +140,14 @@ class Matcher:
     # ------------------------------------------------------------------ lifecycle
     def close(self):
         if self._ctx:
-            self._L.phy_ctx_destroy(self._ctx)
+            if not getattr(self, "_release_at_exit", False):
+                self._L.phy_ctx_destroy(self._ctx)
             self._ctx = C.c_void_p()
+
+    def release_at_exit(self):
+        """One-shot command-line runs: skip the per-buffer cudaFree of close(); the driver releases
+        the whole context when the process exits (freeing ~100 GB index by index costs up to a second)."""
+        self._release_at_exit = True
 
     def __enter__(self):
         return self

@@ -232,6 +232,38 @@ def test_synth_index_and_reads_equal_oracle(M):
     _check_against_oracle(M, i, oidx, records, 0.7, 100)
 
 
+def test_indexes_with_different_hash_counts_resident_together(M, tmp_path):
+    """One match pass over indexes built with 1, 2 and 3 hash functions (same row width class): each is
+    launched with its own AND depth, every unit exact, merged list == closed form over the oracle hits."""
+    _evict_all(M)
+    rnd = random.Random(77)
+    spec = oracle.SynthSpec(seed=31, n_docs=900, genome_len=1500, clade_size=8, clade_sub_q16=500, doc_sub_q16=500)
+    docs = [oracle.synth_genome(spec, d) for d in range(spec.n_docs)]
+    oidxs, ids = {}, {}
+    for nh in (1, 2, 3):
+        o = oracle.OracleIndex.construct(docs, num_hashes=nh, doc_names=[f"{d:05d}_H{nh}D{d:05d}" for d in range(len(docs))])
+        p = os.path.join(tmp_path, f"h{nh}__01.cobs_classic")
+        o.write(p)
+        oidxs[nh] = o
+        ids[nh] = M.load_index(p)
+    records = [(f"r{r}", docs[rnd.randrange(len(docs))][rnd.randrange(0, 300):][:rnd.choice([60, 150, 400, 1200])].decode())
+               for r in range(48)]
+    M.set_queries(records)
+    for thr, top_n in ((0.7, 5), (0.3, 0)):
+        res = M.match(thr, top_n)
+        for nh in (1, 2, 3):
+            units = {int(u["query"]): u for u in res.units_of(ids[nh])}
+            for q, (_, seq) in enumerate(records):
+                n_pass, want = _oracle_unit(oidxs[nh], seq.encode(), thr, top_n)
+                if n_pass == 0:
+                    assert q not in units
+                    continue
+                u = units[q]
+                assert int(u["n_pass"]) == n_pass
+                assert [(int(h["doc"]), int(h["score"])) for h in res.hits_of(u)] == want, (nh, q)
+    _evict_all(M)
+
+
 # --------------------------------------------------------------------------- size-independent properties
 def test_properties_at_scale(M):
     """Config-2-like size (4000 docs): properties that need no oracle run.
@@ -357,10 +389,11 @@ def test_c_abi_state_and_argument_errors(M):
     assert L.phy_ctx_create(C.byref(C.c_void_p()), 4096, 0) == -2                         # no such device
 
 
-@pytest.mark.parametrize("nh,path", [(2, "3"), (1, "1"), (1, "2"), (1, "3")])
-def test_every_query_length_class_on_every_kernel_path(nh, path):
-    """K = 40 .. 20000 (8-, 10-, 14-plane and chunked classes) against an index the ring kernel
-    cannot take (2 hash functions) and on each forced kernel path: no query may be dropped."""
+@pytest.mark.parametrize("nh", [1, 2, 3, 5])
+def test_every_query_length_class_for_every_hash_count(nh):
+    """K = 40 .. 20000 (8-, 10-, 14-plane and chunked classes) against indexes with 1, 2, 3 and 5 hash
+    functions (the ring kernel ANDs the h rows of a k-mer as they leave the ring): no query may be
+    dropped, every score exact."""
     import subprocess, sys
     code = r'''
 import os, sys, random
@@ -382,6 +415,5 @@ _check_against_oracle(m, i, oidx, records, 0.7, 3)
 _check_against_oracle(m, i, oidx, records, 0.2, 0)
 print("ok")
 ''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), nh)
-    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True,
-                       env=dict(os.environ, PHY_KERNEL_PATH=path))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), (r.stdout + r.stderr)[-3000:]
