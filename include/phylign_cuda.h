@@ -57,6 +57,12 @@ int phy_index_begin(phy_ctx* ctx, const char* batch_name, uint32_t term_size,
                     uint8_t canonicalize, uint64_t signature_size, uint64_t num_hashes,
                     uint32_t n_docs, int* idx_id);
 int phy_index_push(phy_ctx* ctx, int idx_id, const void* host_chunk, uint64_t nbytes);
+/* the body of a decompressed `.cobs_classic` file ({decompression_dir}/{batch}.cobs_classic of
+ * Snakefile:364-387) straight from the file to HBM: n_threads readers fill a ring of page-locked
+ * slots, DMA + re-stride on a dedicated upload stream (may run beside phy_match_run of the same
+ * context from another host thread).  body_offset = header length; the file must hold exactly
+ * body_offset + signature_size*row_size bytes.  Follow with phy_index_commit. */
+int phy_index_load_file(phy_ctx* ctx, int idx_id, const char* path, uint64_t body_offset, int n_threads);
 /* fails with PHY_ERR_STATE unless exactly signature_size*row_size bytes arrived */
 int phy_index_commit(phy_ctx* ctx, int idx_id);
 int phy_index_evict(phy_ctx* ctx, int idx_id);

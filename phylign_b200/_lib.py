@@ -101,6 +101,7 @@ PROTOTYPES = {
     "phy_index_begin": (C.c_int, [_P, C.c_char_p, C.c_uint32, C.c_uint8, C.c_uint64, C.c_uint64,
                                   C.c_uint32, C.POINTER(C.c_int)]),
     "phy_index_push": (C.c_int, [_P, C.c_int, C.c_void_p, C.c_uint64]),
+    "phy_index_load_file": (C.c_int, [_P, C.c_int, C.c_char_p, C.c_uint64, C.c_int]),
     "phy_index_commit": (C.c_int, [_P, C.c_int]),
     "phy_index_evict": (C.c_int, [_P, C.c_int]),
     "phy_index_set_ranks": (C.c_int, [_P, C.c_int, C.c_uint32, C.c_void_p]),

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libphylign_cuda.so")
 SOURCES = ["capi.cu", "kmer_hash.cu", "gather_count.cu", "select_merge.cu", "index_store.cu",
-           "nccl_gather.cu", "text_format.cu", "match_writer.cu", "query_io.cu"]
+           "nccl_gather.cu", "text_format.cu", "match_writer.cu", "query_io.cu", "index_loader.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O3,-Wall", "--expt-relaxed-constexpr"]
 

@@ -360,8 +360,16 @@ def cmd_match_db(a):
         _die("--gpus and --shard are alternatives")
     with open(a.batches) as f:
         batches = sorted(filter(len, map(str.strip, f)))      # Snakefile:32-34
-    with tm.span("read_queries_s"):
-        qf = fasta.QueryFile(a.q)                             # flat arrays: no per-record Python objects
+    # the query file is read by a helper thread (native reader, GIL released) while the indexes load
+    from concurrent.futures import ThreadPoolExecutor as _QTPE
+    _qex = _QTPE(max_workers=1)
+
+    def _read_queries():
+        t0 = time.perf_counter()
+        q = fasta.QueryFile(a.q)                              # flat arrays: no per-record Python objects
+        return q, time.perf_counter() - t0
+    qf_future = _qex.submit(_read_queries)
+    q_bytes_bound = os.path.getsize(a.q) * (8 if str(a.q).endswith(".gz") else 1)
     qfile = a.qfile or os.path.splitext(os.path.basename(a.q))[0]
     os.makedirs(a.match_dir, exist_ok=True)
     sizes = {}
@@ -414,14 +422,13 @@ def cmd_match_db(a):
         shard, n_shards = (int(x) for x in a.shard.split("/"))
     if nccl:
         shard, n_shards = rank, world
-    total_bases = qf.total_bases
     t_ctx = time.perf_counter()
     with Matcher(rank if nccl else a.device, a.hbm_budget) as m:
         tm.add("ctx_create_s", time.perf_counter() - t_ctx)
         # HBM left for indexes = the context's budget minus the working set of one query block
         # (hashes 8 B per base, sequence 1 B, unit tables, result/merge buffers)
-        block_bases = min(total_bases, a.query_block_bases)
-        working = 10 * block_bases + 24 * qf.n + (2 << 30)
+        block_bases = min(q_bytes_bound, a.query_block_bases)      # (file size bounds the number of bases)
+        working = 10 * block_bases + 24 * (q_bytes_bound // 32 + 1) + (2 << 30)
         free_for_indexes = max(0, m.budget_bytes() - working)
         budget = min(a.round_bytes, free_for_indexes) if a.round_bytes else int(free_for_indexes * 0.95)
         try:
@@ -442,6 +449,21 @@ def cmd_match_db(a):
             _die("--filter-out needs all batches: use --gpus N, or run `filter` over the match files of all shards")
         collect = want_filter and (not nccl or rank == 0)     # who assembles 04_filter
         brank = sharding.global_batch_ranks(batches)
+        rounds = [sorted(x.name for x in rnd[shard]) for rnd in plan.rounds]
+        loader = _TPE(max_workers=1)                           # index loads run beside everything else
+
+        def load_round(names):
+            t0 = time.perf_counter()
+            ids = m.load_indexes([path_of(b) for b in names], names, workers=a.load_workers,
+                                 keep_paths=[keep_path_of(b) for b in names], active=False) if names else []
+            return ids, time.perf_counter() - t0
+
+        pending_load = loader.submit(load_round, rounds[0]) if rounds else None
+        t0 = time.perf_counter()
+        qf, read_s = qf_future.result()
+        tm.add("read_queries_s", read_s)                      # (thread time; hidden behind the index load)
+        tm.add("read_queries_wait_s", time.perf_counter() - t0)
+        total_bases = qf.total_bases
         # the merge works on the query dict of filter_queries.py:163-176 (readfq names, duplicates
         # collapsed).  For plain FASTA with unique names that is the record list itself.
         qnames = queries = qid = rec2qid = None
@@ -474,16 +496,6 @@ def cmd_match_db(a):
         wstats, gpu_phase_ms, gathered_total, n_writer_blocks = [], np.zeros(3), 0, 0
         direct_merged = direct_arrays = None                   # set when one device merge is already the final answer
         bg = _TPE(max_workers=1)                               # the writer thread (format + gzip + append)
-        loader = _TPE(max_workers=1)                           # next round's indexes (--overlap-rounds)
-        rounds = [sorted(x.name for x in rnd[shard]) for rnd in plan.rounds]
-
-        def load_round(names):
-            t0 = time.perf_counter()
-            ids = m.load_indexes([path_of(b) for b in names], names, workers=a.load_workers,
-                                 keep_paths=[keep_path_of(b) for b in names], active=False) if names else []
-            return ids, time.perf_counter() - t0
-
-        pending_load = None
         try:
             for ri, mine in enumerate(rounds):                 # resident round: load, match, write, evict
                 if pending_load is None:

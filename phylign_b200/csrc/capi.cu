@@ -3,6 +3,7 @@
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
 
 #include <algorithm>
 
@@ -80,6 +81,7 @@ extern "C" int phy_ctx_create(phy_ctx** out, int device, uint64_t hbm_budget) {
         return PHY_ERR_CUDA;
     }
     phy_ctx* ctx = new phy_ctx();
+    ctx->idx.reserve(PHY_MAX_BATCH_RANK);  // entries never move: a file load may run beside a match (index_loader.cu)
     ctx->device = device;
     ctx->n_sm = prop.multiProcessorCount;
     if (getenv("PHY_NO_PRUNE") && atoi(getenv("PHY_NO_PRUNE"))) ctx->prune = false;
@@ -104,11 +106,13 @@ extern "C" int phy_ctx_create(phy_ctx** out, int device, uint64_t hbm_budget) {
 }
 
 void phy_nccl_shutdown(phy_ctx* ctx);
+void phy_loader_destroy(phy_ctx* ctx);
 
 extern "C" void phy_ctx_destroy(phy_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    phy_loader_destroy(ctx);
     // the NCCL communicator is left to process exit: ncclCommDestroy blocks for tens of seconds when
     // the peer ranks tear down at different times (measured), and one ctx lives as long as its process
     for (auto& ix : ctx->idx) {
@@ -183,7 +187,15 @@ void phy_pinned_free(void* p) {
 }
 // result blocks: page-locked from the pool (default) or plain malloc ("pinned_results" 0)
 static void* result_alloc(phy_ctx* ctx, size_t bytes) {
-    return ctx->pinned_results ? phy_pinned_alloc(bytes) : malloc(bytes ? bytes : 1);
+    if (ctx->pinned_results) return phy_pinned_alloc(bytes);
+    if (bytes < (4u << 20)) return malloc(bytes ? bytes : 1);
+    // large one-shot blocks: 2 MB aligned + transparent huge pages, so the first touch by the
+    // download costs one fault per 2 MB instead of one per 4 KB
+    void* p = nullptr;
+    const size_t huge = 2u << 20;
+    if (posix_memalign(&p, huge, (bytes + huge - 1) / huge * huge) != 0) return nullptr;
+    madvise(p, (bytes + huge - 1) / huge * huge, MADV_HUGEPAGE);
+    return p;
 }
 static void result_free(void* p) {
     if (!p) return;
@@ -336,12 +348,21 @@ extern "C" int phy_index_begin(phy_ctx* ctx, const char* batch_name, uint32_t te
     std::vector<uint32_t> ident(n_docs);
     for (uint32_t d = 0; d < n_docs; d++) ident[d] = d;
     PHY_TRY(phy_h2d(ctx, ix.ref_rank_mut, ident.data(), ident.size() * sizeof(uint32_t)));
+    PHY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // rows are zero before any stream (push / file loader) fills them
     ix.alive = true;
     // reuse a dead slot if any
     size_t slot = ctx->idx.size();
     for (size_t i = 0; i < ctx->idx.size(); i++)
         if (!ctx->idx[i].alive) { slot = i; break; }
-    if (slot == ctx->idx.size()) ctx->idx.push_back(HostIndex());
+    if (slot == ctx->idx.size()) {
+        if (ctx->idx.size() >= PHY_MAX_BATCH_RANK) {
+            phy_dev_free(ctx, ix.rows_mut, ix.hbm_bytes, true);
+            phy_dev_free(ctx, ix.ref_rank_mut, (size_t)n_docs * sizeof(uint32_t), true);
+            phy_set_error(ctx, "more than %u indexes in one context", PHY_MAX_BATCH_RANK);
+            return PHY_ERR_ARG;
+        }
+        ctx->idx.push_back(HostIndex());
+    }
     ix.d.idx_id = (uint32_t)slot;
     ix.d.batch_rank = (uint32_t)slot % PHY_MAX_BATCH_RANK;
     ctx->idx[slot] = ix;
@@ -396,6 +417,7 @@ extern "C" int phy_index_commit(phy_ctx* ctx, int idx_id) {
         return PHY_ERR_STATE;
     }
     PHY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->up_stream) PHY_CUDA(ctx, cudaStreamSynchronize(ctx->up_stream));
     ix->committed = true;
     ctx->indexes_dirty = true;
     return PHY_OK;

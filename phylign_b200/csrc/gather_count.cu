@@ -757,6 +757,8 @@ int launch_ring(const GatherArgs& a, cudaStream_t st, int n_sm) {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gather_count_ring_kernel<LPR, P, NB, WARPS, MULTI>,
                                                       WARPS * 32, SMEM) != cudaSuccess || per_sm < 1) return -1;
     constexpr int G = 32 / LPR;
+    static const int cap_per_sm = getenv("PHY_RING_BLOCKS_PER_SM") ? atoi(getenv("PHY_RING_BLOCKS_PER_SM")) : 0;
+    if (cap_per_sm > 0) per_sm = std::min(per_sm, cap_per_sm);   // experiments: leave SM room for a co-running kernel
     uint64_t wunits = ((uint64_t)a.n_class_idx * a.n_q + G - 1) / G;
     uint64_t blocks = std::min<uint64_t>((wunits + WARPS - 1) / WARPS, (uint64_t)n_sm * per_sm);
     if (blocks) gather_count_ring_kernel<LPR, P, NB, WARPS, MULTI><<<(unsigned)blocks, WARPS * 32, SMEM, st>>>(a);
@@ -949,12 +951,15 @@ int phy_launch_gather(phy_ctx* ctx, const phy_match_params* p) {
 
     uint64_t units_cap = ctx->d_units.cap, hits_cap = ctx->d_hits.cap;
     // first sizing guess for a new workload (an overflow is still caught: the pass reports the needed
-    // sizes and is rerun): one unit per 8 (query, index) cells, 64 kept hits per query
+    // sizes and is rerun): one unit per 8 (query, index) cells
     uint64_t n_active_idx = 0;
     for (auto& ix : ctx->idx) n_active_idx += ix.alive && ix.committed && ix.active;
     if (units_cap < 4096)
         units_cap = std::min<uint64_t>(std::max<uint64_t>(1u << 16, (uint64_t)ctx->nq * n_active_idx / 8), 1ull << 24);
-    if (hits_cap < 4096) hits_cap = std::min<uint64_t>(std::max<uint64_t>(1u << 20, 64ull * ctx->nq), 1ull << 27);
+    if (hits_cap < 4096) {  // kept hits per query: ~2 x top_n when a top-N cut applies (ties, a few matching batches)
+        const uint64_t per_q = p->top_n ? std::min<uint64_t>(std::max<uint64_t>(2ull * p->top_n, 64), 256) : 128;
+        hits_cap = std::min<uint64_t>(std::max<uint64_t>(1u << 20, per_q * ctx->nq), 1ull << 28);
+    }
     if (const char* e = getenv("PHY_TEST_TINY_CAPS")) {  // tests: force the overflow -> regrow -> rerun path
         if (atoi(e) && !ctx->d_units.p) { units_cap = 4; hits_cap = 4; }
     }

@@ -190,17 +190,22 @@ __global__ void __launch_bounds__(256) synth_reads_kernel(const phy_synth_spec* 
 
 }  // namespace
 
-int phy_restride_chunk(phy_ctx* ctx, HostIndex& ix, const uint8_t* d_src, uint64_t body_off, uint64_t nbytes) {
+int phy_restride_chunk_on(phy_ctx* ctx, HostIndex& ix, const uint8_t* d_src, uint64_t body_off, uint64_t nbytes,
+                          cudaStream_t st) {
     if (nbytes == 0) return PHY_OK;
     if (ix.d.stride == ix.d.row_size) {
-        PHY_CUDA(ctx, cudaMemcpyAsync(ix.rows_mut + body_off, d_src, nbytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        PHY_CUDA(ctx, cudaMemcpyAsync(ix.rows_mut + body_off, d_src, nbytes, cudaMemcpyDeviceToDevice, st));
         return PHY_OK;
     }
     unsigned blocks = (unsigned)std::min<uint64_t>((nbytes + 255) / 256, 148ull * 16);
-    restride_kernel<<<blocks, 256, 0, ctx->stream>>>(d_src, body_off, nbytes, ix.d.row_size, ix.d.stride, ix.rows_mut);
-    ctx->launches++;
+    restride_kernel<<<blocks, 256, 0, st>>>(d_src, body_off, nbytes, ix.d.row_size, ix.d.stride, ix.rows_mut);
     PHY_CUDA(ctx, cudaGetLastError());
     return PHY_OK;
+}
+
+int phy_restride_chunk(phy_ctx* ctx, HostIndex& ix, const uint8_t* d_src, uint64_t body_off, uint64_t nbytes) {
+    ctx->launches++;
+    return phy_restride_chunk_on(ctx, ix, d_src, body_off, nbytes, ctx->stream);
 }
 
 int phy_destride(phy_ctx* ctx, const HostIndex& ix, uint8_t* d_dst) {

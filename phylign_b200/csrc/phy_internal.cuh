@@ -16,6 +16,7 @@
 #define PHY_FUSED_KMAX ((1u << PHY_FUSED_PLANES) - 1u)
 #define PHY_SHORT_KMAX ((1u << 8) - 1u)   // 8 planes: reads up to 285 bp, pruning checkpoint every 16 rows
 #define PHY_LONG_KMAX ((1u << 14) - 1u)   // 14 planes: fused up to 16383 k-mers (10 kbp reads)
+#define PHY_LD_SLOTS 8                // page-locked 16 MB slots of the index file loader
 #define PHY_CHUNK_BYTES 512u          // one warp-wide 128-bit load = 512 B of a row
 
 // One resident COBS classic index, as the kernels see it.
@@ -73,6 +74,13 @@ struct phy_ctx {
     cudaEvent_t pin_ev[2] = {nullptr, nullptr};
     size_t pin_bytes = 0;
     int pin_cur = 0;
+
+    // file loader (index_loader.cu): own upload stream, page-locked slot ring, device staging
+    bool ld_ready = false;
+    cudaStream_t up_stream = nullptr;
+    uint8_t* ld_pin[PHY_LD_SLOTS] = {};
+    cudaEvent_t ld_ev[PHY_LD_SLOTS] = {};
+    uint8_t* ld_stage[2] = {nullptr, nullptr};
 
     // queries
     bool have_queries = false;

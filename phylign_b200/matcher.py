@@ -186,6 +186,8 @@ class Matcher:
         """Stream a `.cobs_classic[.xz]` file (or pipe) into HBM; returns the index id."""
         if batch is None:
             batch = os.path.basename(str(path)).split(".cobs_classic")[0]
+        if not str(path).endswith(".xz") and os.path.isfile(path):     # plain file: the library's file loader
+            return self.load_indexes([path], [batch], workers=8)[0]
         with IndexStream(path) as st:
             idx_id = self._begin(batch, st.header)
             try:
@@ -212,9 +214,39 @@ class Matcher:
         batches = batches or [os.path.basename(str(p)).split(".cobs_classic")[0] for p in paths]
         keep_paths = keep_paths or [None] * len(paths)
         lock = threading.Lock()
+        file_gate = threading.Lock()
         chunk = 8 << 20
 
+        raw_lib = _lib.load()
+
+        def one_file(path, batch):
+            """Decompressed file: header parsed here, body by the library's file loader (reader threads ->
+            page-locked ring -> DMA + re-stride on the upload stream).  The long call runs outside the
+            Matcher lock: it touches only its own index entry and the upload stream."""
+            st = IndexStream(path)
+            hdr = st.header
+            st.abort()
+            with lock:
+                idx_id = self._begin(batch, hdr)
+                if not active:
+                    self._ck(self._L.phy_index_set_active(self._ctx, idx_id, 0))
+            try:
+                with file_gate:          # one file at a time: the loader parallelises inside
+                    _lib.check(raw_lib.phy_index_load_file(self._ctx, idx_id, os.fsencode(path), hdr.header_size,
+                                                           max(1, workers)), self._ctx)
+                with lock:
+                    self._ck(self._L.phy_index_commit(self._ctx, idx_id))
+            except Exception:
+                with lock:
+                    self._L.phy_index_evict(self._ctx, idx_id)
+                raise
+            with lock:
+                self.indexes[idx_id] = ResidentIndex(idx_id, batch, hdr)
+            return idx_id
+
         def one(path, batch, keep):
+            if not str(path).endswith(".xz") and os.path.isfile(path) and not keep:
+                return one_file(path, batch)
             bufs = [PinnedBuffer(chunk), PinnedBuffer(chunk)]
             tee = None
             with IndexStream(path, chunk_bytes=chunk) as st:
