@@ -155,6 +155,11 @@ typedef struct phy_merged {
  * an empty list with n_queries set). */
 int phy_merged_fetch(phy_ctx* ctx, phy_merged** out);
 void phy_merged_free(phy_merged* m);
+/* Which queries' merged lists this context holds after phy_match_run: [0, nq) on one GPU; with NCCL
+ * either everything on rank 0 ("merge_mode" 0, the default) or one slice of the queries per rank
+ * ("merge_mode" 1: the candidate lists are exchanged all-to-all over NVLink and every rank finalises
+ * and downloads only its slice; offs of phy_merged stays nq+1 long, empty outside the slice). */
+int phy_merged_range(phy_ctx* ctx, uint32_t* q_lo, uint32_t* q_hi);
 /* Merge candidates that come from the host (the `filter_queries.py -n N -q fa match files...`
  * entry: match files parsed by the driver): cands[offs[q] .. offs[q+1]) belong to query q;
  * score, batch_rank (<4096) and ref_rank (<2^20) form the sort key, doc is carried along.
@@ -271,7 +276,9 @@ int phy_last_gather_bytes_of(phy_ctx* ctx, int idx_id, uint64_t* bytes);
 int phy_ctx_budget(phy_ctx* ctx, uint64_t* budget, uint64_t* used);
 /* switches: "prune" 0|1 (exact threshold pruning, default 1; 0 for A/B measurements),
  * "pinned_results" 0|1 (phy_results / phy_merged in page-locked memory from a reuse pool, default 1;
- * 0 = plain host memory, cheaper for a single fetch) */
+ * 0 = plain host memory, cheaper for a single fetch), "merge_mode" 0|1 (multi-GPU: merged lists on rank 0 |
+ * one slice of the queries per rank, see phy_merged_range), "shard_query_upload" 0|1 (multi-GPU, all ranks
+ * pass identical queries: each uploads 1/R of the bases, an NCCL all-gather completes them) */
 int phy_ctx_set_option(phy_ctx* ctx, const char* name, int64_t value);
 /* write a buffer larger than L2 (bench hygiene between timed iterations) */
 int phy_flush_l2(phy_ctx* ctx);

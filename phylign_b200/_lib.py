@@ -119,6 +119,7 @@ PROTOTYPES = {
     "phy_scores": (C.c_int, [_P, C.c_int, C.c_void_p]),
     "phy_merged_fetch": (C.c_int, [_P, C.POINTER(C.POINTER(Merged))]),
     "phy_merged_free": (None, [C.POINTER(Merged)]),
+    "phy_merged_range": (C.c_int, [_P, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "phy_merge_host": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
     "phy_format_cobs_text": (C.c_int, [C.POINTER(Results), C.c_uint32, C.c_char_p, C.c_void_p, C.c_void_p, C.c_char_p,
                                       C.c_void_p, C.c_uint32, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),

@@ -64,6 +64,42 @@ void phy_dev_free(phy_ctx* ctx, void* p, size_t bytes, bool counted) {
     if (counted) ctx->used -= std::min<uint64_t>(ctx->used, bytes ? bytes : 16);
 }
 
+// ---- working-set arena ---------------------------------------------------------------------------
+// The ~25 working buffers of a match pass (hashes, unit tables, hit lists, merge keys ...) are carved
+// out of a few large slabs instead of one cudaMalloc each: a cudaMalloc / cudaFree costs 2-7 ms here
+// regardless of size (measured), which made the first pass of a fresh context ~100 ms slower than the
+// steady state.  Freed blocks go to a size-ordered free list (buffers only ever grow).  Index rows keep
+// their own allocations (they are evicted individually).
+static const size_t WS_SLAB = 256u << 20;
+int phy_ws_alloc(phy_ctx* ctx, void** out, size_t bytes) {
+    bytes = (std::max<size_t>(bytes, 256) + 255) / 256 * 256;
+    auto it = ctx->ws_free.lower_bound(bytes);
+    if (it != ctx->ws_free.end() && it->first <= bytes * 2) {
+        *out = it->second;
+        ctx->ws_free.erase(it);
+        return PHY_OK;
+    }
+    for (auto& sl : ctx->ws_slabs)
+        if (sl.cap - sl.bump >= bytes) {
+            *out = sl.base + sl.bump;
+            sl.bump += bytes;
+            ctx->ws_size[*out] = bytes;
+            return PHY_OK;
+        }
+    const size_t cap = bytes > WS_SLAB / 2 ? bytes : WS_SLAB;
+    void* p = nullptr;
+    PHY_TRY(phy_dev_alloc(ctx, &p, cap, true));
+    ctx->ws_slabs.push_back(phy_ctx::WsSlab{(uint8_t*)p, cap, bytes});
+    ctx->ws_size[p] = bytes;
+    *out = p;
+    return PHY_OK;
+}
+void phy_ws_free(phy_ctx* ctx, void* p) {
+    if (!p) return;
+    auto it = ctx->ws_size.find(p);
+    if (it != ctx->ws_size.end()) ctx->ws_free.insert({it->second, p});
+}
+
 static const size_t PIN_BYTES = 32u << 20;
 
 extern "C" int phy_ctx_create(phy_ctx** out, int device, uint64_t hbm_budget) {
@@ -119,13 +155,7 @@ extern "C" void phy_ctx_destroy(phy_ctx* ctx) {
         if (ix.rows_mut) cudaFree(ix.rows_mut);
         if (ix.ref_rank_mut) cudaFree(ix.ref_rank_mut);
     }
-    void* bufs[] = {ctx->d_indexes.p, ctx->d_seq.p, ctx->d_qoffs.p, ctx->d_koffs.p, ctx->d_hashes.p, ctx->d_nk.p,
-                    ctx->d_T.p, ctx->d_qlist.p, ctx->d_class.p, ctx->d_units.p, ctx->d_hits.p, ctx->d_counters.p,
-                    ctx->d_qcount.p, ctx->d_scores.p, ctx->d_items.p, ctx->d_slotq.p, ctx->d_ckey.p, ctx->d_qoffs_c.p,
-                    ctx->d_foffs.p, ctx->d_scan_tmp.p, ctx->d_cval.p, ctx->d_qcursor.p, ctx->d_nfinal.p,
-                    ctx->d_final.p, ctx->d_flush.p, ctx->d_foffs_all.p, ctx->d_rank_base.p,
-                    ctx->d_idx_bytes.p, ctx->d_recv.p, ctx->d_units_sorted.p, ctx->d_unit_flag.p, ctx->d_unit_id.p, ctx->d_unit_pos.p, ctx->d_ioffs.p};
-    for (void* b : bufs) if (b) cudaFree(b);
+    for (auto& sl : ctx->ws_slabs) cudaFree(sl.base);  // every working buffer lives in these
     for (int i = 0; i < 2; i++) {
         if (ctx->pin[i]) cudaFreeHost(ctx->pin[i]);
         if (ctx->d_stage[i]) cudaFree(ctx->d_stage[i]);
@@ -533,9 +563,21 @@ extern "C" int phy_queries_set(phy_ctx* ctx, const char* seq_concat, const uint6
     ctx->hashes_valid = false;
     ctx->have_match = ctx->have_merged = false;
     ctx->q_term_size = 0;  // k-mer tables are (re)built by phy_match_run for the resident indexes' k
-    PHY_TRY(phy_ensure(ctx, ctx->d_seq, ctx->total_bases + 64));
     PHY_TRY(phy_ensure(ctx, ctx->d_qoffs, nq + 2));
-    if (ctx->total_bases) PHY_TRY(phy_h2d(ctx, ctx->d_seq.p, seq_concat + offs[0], ctx->total_bases));
+    if (ctx->shard_query_upload && ctx->n_ranks > 1 && ctx->total_bases >= (1u << 20)) {
+        // every rank of the job passes the same queries: upload 1/R of the bases over this GPU's PCIe
+        // link and let the slices meet over NVLink (R x less host traffic per step)
+        const uint64_t R = (uint64_t)ctx->n_ranks;
+        const uint64_t slice = ((ctx->total_bases + R - 1) / R + 255) / 256 * 256;
+        PHY_TRY(phy_ensure(ctx, ctx->d_seq, slice * R + 64));
+        const uint64_t lo = std::min<uint64_t>(slice * (uint64_t)ctx->rank, ctx->total_bases);
+        const uint64_t hi = std::min<uint64_t>(lo + slice, ctx->total_bases);
+        if (hi > lo) PHY_TRY(phy_h2d(ctx, ctx->d_seq.p + lo, seq_concat + offs[0] + lo, hi - lo));
+        PHY_TRY(phy_nccl_allgather_inplace(ctx, ctx->d_seq.p, slice));
+    } else {
+        PHY_TRY(phy_ensure(ctx, ctx->d_seq, ctx->total_bases + 64));
+        if (ctx->total_bases) PHY_TRY(phy_h2d(ctx, ctx->d_seq.p, seq_concat + offs[0], ctx->total_bases));
+    }
     if (offs[0] != 0)
         for (auto& o : ctx->h_qoffs) o -= offs[0];
     PHY_TRY(phy_h2d(ctx, ctx->d_qoffs.p, ctx->h_qoffs.data(), (nq + 1) * sizeof(uint64_t)));
@@ -729,7 +771,7 @@ extern "C" int phy_merged_fetch(phy_ctx* ctx, phy_merged** out) {
     phy_merged* m = (phy_merged*)calloc(1, sizeof(phy_merged));
     if (!m) return PHY_ERR_NOMEM;
     m->n_queries = ctx->nq;
-    const bool holder = ctx->n_ranks == 1 || ctx->rank == 0;
+    const bool holder = ctx->n_ranks == 1 || ctx->rank == 0 || ctx->merge_sharded;
     const uint64_t n = holder ? ctx->n_final : 0;
     m->offs = (uint64_t*)result_alloc(ctx, ((size_t)ctx->nq + 1) * sizeof(uint64_t));
     m->cands = (phy_cand*)result_alloc(ctx, std::max<uint64_t>(1, n) * sizeof(phy_cand));
@@ -814,6 +856,16 @@ extern "C" int phy_last_gather_bytes(phy_ctx* ctx, uint64_t* bytes) {
     *bytes = ctx->gathered_bytes;
     return PHY_OK;
 }
+extern "C" int phy_merged_range(phy_ctx* ctx, uint32_t* q_lo, uint32_t* q_hi) {
+    if (!ctx || !q_lo || !q_hi) return PHY_ERR_ARG;
+    if (!ctx->have_merged) {
+        phy_set_error(ctx, "no merged result");
+        return PHY_ERR_STATE;
+    }
+    *q_lo = ctx->n_ranks > 1 ? ctx->merged_q_lo : 0;
+    *q_hi = ctx->n_ranks > 1 ? ctx->merged_q_hi : ctx->nq;
+    return PHY_OK;
+}
 extern "C" int phy_last_gather_bytes_of(phy_ctx* ctx, int idx_id, uint64_t* bytes) {
     if (!ctx || !bytes || idx_id < 0) return PHY_ERR_ARG;
     *bytes = (size_t)idx_id < ctx->h_idx_bytes.size() ? ctx->h_idx_bytes[idx_id] : 0;
@@ -829,6 +881,8 @@ extern "C" int phy_ctx_set_option(phy_ctx* ctx, const char* name, int64_t value)
     if (!ctx || !name) return PHY_ERR_ARG;
     if (!strcmp(name, "prune")) ctx->prune = value != 0;
     else if (!strcmp(name, "pinned_results")) ctx->pinned_results = value != 0;
+    else if (!strcmp(name, "merge_mode") && (value == 0 || value == 1)) ctx->merge_sharded = value == 1;
+    else if (!strcmp(name, "shard_query_upload")) ctx->shard_query_upload = value != 0;
     else {
         phy_set_error(ctx, "unknown option %s=%lld", name, (long long)value);
         return PHY_ERR_ARG;
@@ -841,7 +895,7 @@ extern "C" int phy_flush_l2(phy_ctx* ctx) {
     PHY_CUDA(ctx, cudaSetDevice(ctx->device));
     if (!ctx->d_flush.p) {
         void* p = nullptr;
-        PHY_TRY(phy_dev_alloc(ctx, &p, n, true));
+        PHY_TRY(phy_ws_alloc(ctx, &p, n));
         ctx->d_flush.p = (uint8_t*)p;
         ctx->d_flush.cap = n;
     }

@@ -27,7 +27,7 @@ int phy_restride_chunk_on(phy_ctx* ctx, HostIndex& ix, const uint8_t* d_src, uin
                           cudaStream_t st);
 
 namespace {
-constexpr size_t LD_CHUNK = 16u << 20;
+constexpr size_t LD_CHUNK = 4u << 20;
 
 int ensure_loader(phy_ctx* ctx) {
     if (ctx->ld_ready) return PHY_OK;

@@ -108,7 +108,61 @@ __global__ void __launch_bounds__(128) regroup_kernel(const uint64_t* __restrict
     }
 }
 
+// ---- query-sharded merge: rank s finalises queries [qb[s], qb[s+1]) -----------------------------
+// B[r][s] = foffs_all[r][qb[s]]: where rank r's candidates for rank s's queries start
+__global__ void shard_bounds_kernel(const uint64_t* __restrict__ foffs_all, uint32_t n_ranks, uint32_t nq,
+                                    uint64_t* __restrict__ bounds) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_ranks * (n_ranks + 1)) return;
+    const uint32_t r = t / (n_ranks + 1), s = t % (n_ranks + 1);
+    const uint32_t qb = (uint32_t)((uint64_t)nq * s / n_ranks);
+    bounds[t] = foffs_all[(uint64_t)r * (nq + 1) + qb];
+}
+__global__ void __launch_bounds__(256) rank_totals_range_kernel(const uint64_t* __restrict__ foffs_all, uint32_t n_ranks,
+                                                                uint32_t nq, uint32_t q_lo, uint32_t q_hi,
+                                                                uint32_t* __restrict__ totals) {
+    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    uint64_t t = 0;
+    if (q >= q_lo && q < q_hi)
+        for (uint32_t r = 0; r < n_ranks; r++) {
+            const uint64_t* f = foffs_all + (uint64_t)r * (nq + 1);
+            t += f[q + 1] - f[q];
+        }
+    totals[q] = (uint32_t)t;
+}
+// recv holds, rank after rank, every rank's candidates for queries [q_lo, q_hi)
+__global__ void __launch_bounds__(128) regroup_range_kernel(const uint64_t* __restrict__ foffs_all,
+                                                            const uint64_t* __restrict__ rank_base, uint32_t n_ranks,
+                                                            uint32_t nq, uint32_t q_lo, uint32_t q_hi,
+                                                            const phy_cand* __restrict__ recv,
+                                                            const uint64_t* __restrict__ qoffs_c,
+                                                            uint64_t* __restrict__ ckey, uint32_t* __restrict__ cval) {
+    for (uint32_t q = q_lo + blockIdx.x; q < q_hi; q += gridDim.x) {
+        uint64_t dst = qoffs_c[q];
+        for (uint32_t r = 0; r < n_ranks; r++) {
+            const uint64_t* f = foffs_all + (uint64_t)r * (nq + 1);
+            const uint64_t src = rank_base[r] + (f[q] - f[q_lo]);
+            const uint32_t n = (uint32_t)(f[q + 1] - f[q]);
+            for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+                phy_cand c = recv[src + i];
+                ckey[dst + i] = ((uint64_t)(~c.score) << 32) | ((uint64_t)c.batch_rank << 20) | c.ref_rank;
+                cval[dst + i] = c.doc;
+            }
+            dst += n;
+        }
+    }
+}
+
 }  // namespace
+
+// queries' bases: every rank uploads 1/R of them over its own PCIe link, the slices meet over NVLink
+int phy_nccl_allgather_inplace(phy_ctx* ctx, void* buf, size_t slice_bytes) {
+    ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
+    PHY_NCCL(ctx, g_nccl.AllGather((const uint8_t*)buf + (size_t)ctx->rank * slice_bytes, buf, slice_bytes, ncclChar,
+                                   comm, ctx->stream));
+    return PHY_OK;
+}
 
 extern "C" int phy_nccl_unique_id(void* id_out) {
     if (!id_out) return PHY_ERR_ARG;
@@ -141,10 +195,71 @@ void phy_nccl_shutdown(phy_ctx* ctx) {
     ctx->rank = 0;
 }
 
+// Query-sharded variant: rank s receives every rank's candidates for ITS slice of the queries
+// (all-to-all over NVLink) and finalises those; the merged lists stay distributed over the ranks
+// (phy_merged_range tells which queries a rank holds).  The merge work and the final download then
+// shrink with the number of GPUs instead of piling up on rank 0.
+static int nccl_merge_sharded(phy_ctx* ctx, uint32_t top_n) {
+    ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
+    const uint32_t nq = ctx->nq, R = (uint32_t)ctx->n_ranks, me = (uint32_t)ctx->rank;
+    auto qb = [&](uint32_t s) { return (uint32_t)((uint64_t)nq * s / R); };
+    DevBuf<uint64_t>& all = ctx->d_foffs_all;
+    PHY_TRY(phy_ensure(ctx, all, (size_t)R * (nq + 1) + (size_t)R * (R + 1)));
+    uint64_t* d_bounds = all.p + (size_t)R * (nq + 1);
+    PHY_NCCL(ctx, g_nccl.AllGather(ctx->d_foffs.p, all.p, nq + 1, ncclUint64, comm, ctx->stream));
+    shard_bounds_kernel<<<(R * (R + 1) + 127) / 128, 128, 0, ctx->stream>>>(all.p, R, nq, d_bounds);
+    ctx->launches++;
+    std::vector<uint64_t> B((size_t)R * (R + 1));
+    PHY_CUDA(ctx, cudaMemcpyAsync(B.data(), d_bounds, B.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    PHY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    auto bound = [&](uint32_t r, uint32_t s) { return B[(size_t)r * (R + 1) + s]; };
+    std::vector<uint64_t> base(R + 1, 0);
+    for (uint32_t r = 0; r < R; r++) base[r + 1] = base[r] + (bound(r, me + 1) - bound(r, me));
+    PHY_TRY(phy_ensure(ctx, ctx->d_recv, base[R] + 1));
+    static_assert(sizeof(phy_cand) == 16, "phy_cand is sent as 4 x uint32");
+    PHY_NCCL(ctx, g_nccl.GroupStart());
+    for (uint32_t s = 0; s < R; s++) {
+        if (s == me) continue;
+        const uint64_t n_to = bound(me, s + 1) - bound(me, s), n_from = base[s + 1] - base[s];
+        if (n_to) PHY_NCCL(ctx, g_nccl.Send(ctx->d_final.p + bound(me, s), n_to * 4, ncclUint32, (int)s, comm, ctx->stream));
+        if (n_from) PHY_NCCL(ctx, g_nccl.Recv(ctx->d_recv.p + base[s], n_from * 4, ncclUint32, (int)s, comm, ctx->stream));
+    }
+    PHY_NCCL(ctx, g_nccl.GroupEnd());
+    if (base[me + 1] > base[me])
+        PHY_CUDA(ctx, cudaMemcpyAsync(ctx->d_recv.p + base[me], ctx->d_final.p + bound(me, me),
+                                      (base[me + 1] - base[me]) * sizeof(phy_cand), cudaMemcpyDeviceToDevice, ctx->stream));
+    const uint32_t q_lo = qb(me), q_hi = qb(me + 1);
+    PHY_TRY(phy_ensure(ctx, ctx->d_rank_base, R + 1));
+    PHY_TRY(phy_h2d(ctx, ctx->d_rank_base.p, base.data(), (R + 1) * sizeof(uint64_t)));
+    PHY_TRY(phy_ensure(ctx, ctx->d_qcount, nq + 1));
+    if (nq) {
+        rank_totals_range_kernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(all.p, R, nq, q_lo, q_hi, ctx->d_qcount.p);
+        ctx->launches++;
+    }
+    uint64_t total = 0;
+    PHY_TRY(phy_ensure(ctx, ctx->d_qoffs_c, nq + 2));
+    PHY_TRY(phy_exscan(ctx, ctx->d_qcount.p, nq, ctx->d_qoffs_c.p, &total));
+    PHY_TRY(phy_ensure(ctx, ctx->d_ckey, total + 1));
+    PHY_TRY(phy_ensure(ctx, ctx->d_cval, total + 1));
+    if (q_hi > q_lo && total) {
+        unsigned blocks = (unsigned)std::min<uint64_t>(q_hi - q_lo, 148ull * 32);
+        regroup_range_kernel<<<blocks, 128, 0, ctx->stream>>>(all.p, ctx->d_rank_base.p, R, nq, q_lo, q_hi, ctx->d_recv.p,
+                                                             ctx->d_qoffs_c.p, ctx->d_ckey.p, ctx->d_cval.p);
+        ctx->launches++;
+        PHY_CUDA(ctx, cudaGetLastError());
+    }
+    ctx->merged_q_lo = q_lo;
+    ctx->merged_q_hi = q_hi;
+    return phy_merge_segments(ctx, top_n);
+}
+
 // After the local merge: gather every rank's (d_foffs, d_final) on rank 0 and merge again.
 int phy_nccl_merge(phy_ctx* ctx, uint32_t top_n) {
+    if (ctx->merge_sharded) return nccl_merge_sharded(ctx, top_n);
     ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
     const uint32_t nq = ctx->nq, R = (uint32_t)ctx->n_ranks;
+    ctx->merged_q_lo = 0;
+    ctx->merged_q_hi = ctx->rank == 0 ? nq : 0;
     // (1) every rank learns every rank's per-query offsets (tiny: R x (nq+1) x 8 B)
     DevBuf<uint64_t>& all = ctx->d_foffs_all;
     PHY_TRY(phy_ensure(ctx, all, (size_t)R * (nq + 1)));

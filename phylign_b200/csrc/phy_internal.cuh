@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <map>
 #include <string>
 #include <vector>
 
@@ -16,7 +17,7 @@
 #define PHY_FUSED_KMAX ((1u << PHY_FUSED_PLANES) - 1u)
 #define PHY_SHORT_KMAX ((1u << 8) - 1u)   // 8 planes: reads up to 285 bp, pruning checkpoint every 16 rows
 #define PHY_LONG_KMAX ((1u << 14) - 1u)   // 14 planes: fused up to 16383 k-mers (10 kbp reads)
-#define PHY_LD_SLOTS 8                // page-locked 16 MB slots of the index file loader
+#define PHY_LD_SLOTS 16               // page-locked 4 MB slots of the index file loader
 #define PHY_CHUNK_BYTES 512u          // one warp-wide 128-bit load = 512 B of a row
 
 // One resident COBS classic index, as the kernels see it.
@@ -63,6 +64,10 @@ struct phy_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_ph[4] = {nullptr, nullptr, nullptr, nullptr};
     uint64_t budget = 0, used = 0;
+    struct WsSlab { uint8_t* base; size_t cap, bump; };
+    std::vector<WsSlab> ws_slabs;              // working-set arena (capi.cu: phy_ws_alloc)
+    std::multimap<size_t, void*> ws_free;      // freed arena blocks by size
+    std::map<void*, size_t> ws_size;
     std::string err;
     std::vector<HostIndex> idx;
     DevBuf<DevIndex> d_indexes;  // mirrors idx[] (dead slots zeroed)
@@ -124,6 +129,9 @@ struct phy_ctx {
     DevBuf<phy_cand> d_recv;
     void* nccl_comm = nullptr;
     int rank = 0, n_ranks = 1;
+    bool merge_sharded = false;        // "merge_mode" 1: every rank finalises its slice of the queries
+    bool shard_query_upload = false;   // every rank uploads 1/R of the bases, NCCL all-gather completes them
+    uint32_t merged_q_lo = 0, merged_q_hi = 0;  // queries whose merged lists this context holds
 };
 
 // ---- error helpers ---------------------------------------------------------------
@@ -145,15 +153,17 @@ void phy_set_error(phy_ctx* ctx, const char* fmt, ...);
 
 int phy_dev_alloc(phy_ctx* ctx, void** p, size_t bytes, bool counted);
 void phy_dev_free(phy_ctx* ctx, void* p, size_t bytes, bool counted);
+int phy_ws_alloc(phy_ctx* ctx, void** p, size_t bytes);   // working buffers: carved from large slabs
+void phy_ws_free(phy_ctx* ctx, void* p);
 template <class T>
 int phy_ensure(phy_ctx* ctx, DevBuf<T>& b, size_t n) {
     if (n <= b.cap && b.p) return PHY_OK;
     size_t want = n + n / 4 + 16;
-    if (b.p) phy_dev_free(ctx, b.p, b.cap * sizeof(T), true);
+    if (b.p) phy_ws_free(ctx, b.p);
     b.p = nullptr;
     b.cap = 0;
     void* p = nullptr;
-    int r = phy_dev_alloc(ctx, &p, want * sizeof(T), true);
+    int r = phy_ws_alloc(ctx, &p, want * sizeof(T));
     if (r != PHY_OK) return r;
     b.p = (T*)p;
     b.cap = want;
@@ -161,7 +171,7 @@ int phy_ensure(phy_ctx* ctx, DevBuf<T>& b, size_t n) {
 }
 template <class T>
 void phy_release(phy_ctx* ctx, DevBuf<T>& b) {
-    if (b.p) phy_dev_free(ctx, b.p, b.cap * sizeof(T), true);
+    if (b.p) phy_ws_free(ctx, b.p);
     b.p = nullptr;
     b.cap = 0;
 }
@@ -177,6 +187,7 @@ int phy_launch_scores(phy_ctx* ctx, int idx_id, uint32_t* d_out_scores);
 int phy_launch_sort_units(phy_ctx* ctx);
 int phy_launch_merge(phy_ctx* ctx, uint32_t top_n);
 int phy_nccl_merge(phy_ctx* ctx, uint32_t top_n);
+int phy_nccl_allgather_inplace(phy_ctx* ctx, void* buf, size_t slice_bytes);
 int phy_merge_segments(phy_ctx* ctx, uint32_t top_n);
 int phy_exscan(phy_ctx* ctx, const uint32_t* d_in, uint64_t n, uint64_t* d_out, uint64_t* total_host);
 int phy_lpr_for_stride(uint32_t stride);

@@ -249,7 +249,7 @@ int phy_order_units(phy_ctx* ctx, uint64_t cells) {
     if (ctx->d_units_sorted.cap != ctx->d_units.cap) {  // twin of d_units: exactly the same capacity (they swap)
         phy_release(ctx, ctx->d_units_sorted);
         void* p = nullptr;
-        PHY_TRY(phy_dev_alloc(ctx, &p, ctx->d_units.cap * sizeof(phy_unit), true));
+        PHY_TRY(phy_ws_alloc(ctx, &p, ctx->d_units.cap * sizeof(phy_unit)));
         ctx->d_units_sorted.p = (phy_unit*)p;
         ctx->d_units_sorted.cap = ctx->d_units.cap;
     }

@@ -462,6 +462,12 @@ class Matcher:
         self._merged_owner = owner
         return offs, cands
 
+    def merged_range(self):
+        """(q_lo, q_hi): the queries whose merged lists this rank holds (see phy_merged_range)."""
+        lo, hi = C.c_uint32(), C.c_uint32()
+        self._ck(self._L.phy_merged_range(self._ctx, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
     def merge_host(self, offs: np.ndarray, cands: np.ndarray, top_n: int):
         """filter_queries.py entry: merge host-supplied candidates (CAND_DT, grouped by query)."""
         offs = np.ascontiguousarray(offs, dtype=np.uint64)
