@@ -458,6 +458,13 @@ class Dist:
         self.d.all_reduce(t, op=self.d.ReduceOp.MAX)
         return float(t[0])
 
+    def sum(self, x):
+        if self.d is None:
+            return x
+        t = self.torch.tensor([float(x)], dtype=self.torch.float64)
+        self.d.all_reduce(t, op=self.d.ReduceOp.SUM)
+        return float(t[0])
+
     def gather(self, obj):
         """[obj of every rank] on rank 0 (None elsewhere)."""
         if self.d is None:
@@ -472,6 +479,46 @@ class Dist:
         box = [obj]
         self.d.broadcast_object_list(box, src=0)
         return box[0]
+
+
+def multi_gpu_options(m, args):
+    """N > 1: every rank finalises and downloads its own slice of the queries' merged lists and uploads
+    1/N of the bases (all-gather over NVLink) -- what `match-db --gpus N` does too."""
+    m.set_option("merge_mode", 0 if args.merge_on_rank0 else 1)
+    m.set_option("shard_query_upload", 0 if args.merge_on_rank0 else 1)
+
+
+def full_merged(dist, m, moffs, mcands):
+    """(offs, cands) of ALL queries on rank 0 (None elsewhere): the ranks' slices joined in query order
+    when the merge is query-sharded.  Control-plane traffic, outside every timed region."""
+    if dist.world == 1:
+        return np.asarray(moffs), np.asarray(mcands)
+    lo, hi = m.merged_range()
+    o = np.asarray(moffs).astype(np.int64)
+    parts = dist.gather((lo, hi, o[lo:hi + 1] - o[lo], np.array(mcands)))
+    if dist.rank != 0:
+        return None, None
+    parts = sorted((p for p in parts if p[1] > p[0]), key=lambda p: p[0])
+    nq = len(o) - 1
+    offs = np.zeros(nq + 1, dtype=np.uint64)
+    cands, run = [], 0
+    for lo, hi, po, pc in parts:
+        offs[lo:hi + 1] = (po + run).astype(np.uint64)
+        run += int(po[-1])
+        offs[hi:] = run
+        cands.append(pc)
+    return offs, (np.concatenate(cands) if cands else np.array(mcands)[:0])
+
+
+def merged_struct(offs, cands):
+    """A phy_merged over host arrays (for the library's formatters); keep the arrays alive while it is used."""
+    import ctypes as C
+    from phylign_b200 import _lib
+    offs = np.ascontiguousarray(offs, dtype=np.uint64)
+    cands = np.ascontiguousarray(cands)
+    st = _lib.Merged(len(offs) - 1, C.cast(offs.ctypes.data, C.POINTER(C.c_uint64)),
+                     C.cast(cands.ctypes.data, C.POINTER(_lib.Cand)), 0)
+    return st, (offs, cands)
 
 
 def unit_hits_in_order(res):
@@ -509,6 +556,7 @@ def result_digest(dist, m, res, moffs, mcands):
     """sha256 over the per-batch digests in batch-rank order + the merged lists: independent of the
     number of GPUs and of the placement (idx ids are local, batch ranks are global)."""
     parts = dist.gather(local_digests(m, res))
+    moffs, mcands = full_merged(dist, m, moffs, mcands)
     if dist.rank != 0:
         return None
     allb = {}
@@ -559,7 +607,7 @@ def pinned_queries(raw, offs):
     return pr, po
 
 
-def e2e_steps(dist, m, pin_raw, pin_offs, raw_len, offs_bytes, steps, warmup):
+def e2e_steps(dist, m, pin_raw, pin_offs, raw_len, offs_bytes, steps, warmup, sharded_upload=False):
     for _ in range(max(2, warmup)):   # warm-up: the pinned result pool reaches its steady state after 2 passes
         m.set_queries_raw(pin_raw, pin_offs)
         m.match_run(THRESHOLD, TOP_N, merge_top_n=TOP_N)
@@ -581,7 +629,7 @@ def e2e_steps(dist, m, pin_raw, pin_offs, raw_len, offs_bytes, steps, warmup):
         moffs, mcands = m.merged()                         # D2H: merged top-N lists (04_filter content)
         te = time.perf_counter()
         parts += [tb - ta, tc - tb, td - tc, te - td]
-        h2d = raw_len + offs_bytes
+        h2d = (raw_len + dist.world - 1) // dist.world + offs_bytes if sharded_upload else raw_len + offs_bytes
         d2h = res.d2h_bytes + moffs.nbytes + mcands.nbytes
     m.sync()
     e2e_s = dist.max((time.perf_counter() - t0) / steps)
@@ -663,6 +711,7 @@ def run_ours(args, w, rank, world, local_rank):
     m = Matcher(local_rank)
     if world > 1:
         m.nccl_init(dist.bcast(nccl_unique_id() if rank == 0 else None), rank, world)
+        multi_gpu_options(m, args)
     specs = [_lib.SynthSpec(**spec_kwargs(b)) for b in w["batches"]]
     placement, imbalance = place(w, world, args.hbm_budget_gb * 10 ** 9)
     t_build = time.perf_counter()
@@ -687,11 +736,13 @@ def run_ours(args, w, rank, world, local_rank):
     value = w["bases"] / (ms_per_step * 1e-3)
 
     # ---- end to end through the public API: host buffers in, host results out, every step
+    sharded = world > 1 and not args.merge_on_rank0
     e2e_s, h2d, d2h, e2e_parts, res, moffs, mcands = e2e_steps(dist, m, pin_raw, pin_offs, len(raw), offs.nbytes,
-                                                               args.steps, args.warmup)
+                                                               args.steps, args.warmup, sharded)
+    h2d_all, d2h_all = dist.sum(h2d), dist.sum(d2h)             # whole job (all ranks)
     e2e_value = w["bases"] / e2e_s
     digest = result_digest(dist, m, res, moffs, mcands)
-    n_units, n_hits, n_merged = int(len(res.units)), int(len(res.hits)), int(len(mcands))
+    n_units, n_hits, n_merged = int(dist.sum(len(res.units))), int(dist.sum(len(res.hits))), int(dist.sum(len(mcands)))
     want_files = (not args.no_e2e_files) and w["name"] == "reads1k"
     exp_files = exp_fa = None
     if want_files:      # what the files must hold, from these very device results
@@ -699,9 +750,14 @@ def run_ours(args, w, rank, world, local_rank):
         records = [(names[i], raw[i * L:(i + 1) * L]) for i in range(w["n_reads"])]
         refs_by_rank = {br: [f"SYN{d:06d}" for d in range(b["n_docs"])]
                         for br, b in enumerate(sorted(w["batches"], key=lambda b: b["name"]))}
-        exp_files, exp_fa = expected_file_digests(m, records, res, m._merged_owner if rank == 0 else None,
-                                                  all_names, refs_by_rank)
-        del records
+        fo, fc = full_merged(dist, m, moffs, mcands)
+        mstruct = keep = None
+        if rank == 0:
+            import ctypes as C
+            mstruct, keep = merged_struct(fo, fc)
+            mstruct = type("P", (), {"ptr": C.pointer(mstruct)})()
+        exp_files, exp_fa = expected_file_digests(m, records, res, mstruct, all_names, refs_by_rank)
+        del records, keep, fo, fc
     del res, moffs, mcands
 
     # ---- the same gather with the exact threshold pruning switched off (explains the roofline)
@@ -842,7 +898,10 @@ def run_ours(args, w, rank, world, local_rank):
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": config_dict(w),
             "run": {"sharding": f"indexes placed LPT-by-row-bytes on {world} GPU(s) (imbalance {imbalance:.3f}), "
-                                f"queries replicated",
+                                f"queries replicated" + ("" if world == 1 else
+                                                         (", merged lists on rank 0" if args.merge_on_rank0 else
+                                                          f"; each rank uploads 1/{world} of the bases (NVLink all-gather) and "
+                                                          f"finalises + downloads 1/{world} of the queries' merged lists")),
                     "index_build_s": round(t_build, 2),
                     "kmer_docs_per_s": w["kmer_docs"] / (ms_per_step * 1e-3),
                     "phase_ms_hash_gather_merge": main["phases"],
@@ -871,8 +930,9 @@ def run_ours(args, w, rank, world, local_rank):
                                       "what": "same launch with pruning off: every pair gathered"},
                          "note": f"row bytes gathered by rank 0's launch / mean CUDA-event duration of the "
                                  f"gather phase ({g_ms:.2f} ms, one launch per step); peak = {peak_src}"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_s * 1e3, "breakdown_ms_set_run_fetch_merged": e2e_parts},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_all), "d2h_bytes_per_step": int(d2h_all),
+                    "ms_per_step": e2e_s * 1e3, "breakdown_ms_set_run_fetch_merged": e2e_parts,
+                    "bytes_are": "summed over all ranks (each rank copies its share of the queries / results)"},
             "e2e_files": e2e_files,
             "secondary": secondary,
             "gpu_launches": main["launches"], "clocks": main["clocks"]}
@@ -918,6 +978,7 @@ def secondary_db661k(args, dist, rank, world, local_rank):
     w = workload(a2)
     m = Matcher(local_rank)
     m.nccl_init(dist.bcast(nccl_unique_id() if rank == 0 else None), rank, world)
+    multi_gpu_options(m, args)
     placement, imbalance = place(w, world, args.hbm_budget_gb * 10 ** 9)
     t0 = time.perf_counter()
     for b in placement[rank]:
@@ -933,7 +994,9 @@ def secondary_db661k(args, dist, rank, world, local_rank):
     steps = 5
     t = timed_steps(dist, m, steps, 3, rank, local_rank)
     pin_raw, pin_offs = pinned_queries(raw, offs)
-    e2e_s, h2d, d2h, parts, res, moffs, mcands = e2e_steps(dist, m, pin_raw, pin_offs, len(raw), offs.nbytes, steps, 2)
+    e2e_s, h2d, d2h, parts, res, moffs, mcands = e2e_steps(dist, m, pin_raw, pin_offs, len(raw), offs.nbytes, steps, 2,
+                                                           not args.merge_on_rank0)
+    h2d, d2h = dist.sum(h2d), dist.sum(d2h)
     dg = result_digest(dist, m, res, moffs, mcands)
     del res, moffs, mcands
     m.set_option("prune", 0)
@@ -986,6 +1049,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e-files", action="store_true", help="skip the files-in -> files-out run of match-db")
     ap.add_argument("--no-db661k", action="store_true", help="at --gpus 8: skip secondary.db661k")
+    ap.add_argument("--merge-on-rank0", action="store_true",
+                    help="N > 1: gather the merged lists on rank 0 and replicate the query upload (round-1 behaviour)")
     ap.add_argument("--workdir", default=None, help=argparse.SUPPRESS)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))

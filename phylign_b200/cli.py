@@ -250,6 +250,10 @@ def _spawn_match_db_workers(a):
     import subprocess
     import tempfile
     import time
+    if a.filter_out:                           # parts of an earlier, interrupted run must not be joined
+        import glob
+        for p in glob.glob(glob.escape(a.filter_out) + ".part.*"):
+            os.unlink(p)
     tmpdir = tempfile.mkdtemp(prefix="phylign_nccl_")
     id_file = os.path.join(tmpdir, "id")
     argv = [x for x in sys.argv[1:]]
@@ -281,6 +285,19 @@ def _spawn_match_db_workers(a):
                     p.wait()
             _die(f"match-db worker {failed} failed (exit code {procs[failed].returncode}); "
                  f"the other workers were stopped")
+        if a.filter_out:                       # query-sharded merge: every worker left its slices as parts
+            import glob
+            parts = sorted(glob.glob(glob.escape(a.filter_out) + ".part.*"))
+            parts = [p for p in parts if ".tmp." not in p]
+            if parts:
+                tmp = f"{a.filter_out}.tmp.{os.getpid()}"
+                with open(tmp, "wb") as out:
+                    for p in parts:             # names sort by (block, rank) = query order
+                        with open(p, "rb") as f:
+                            shutil.copyfileobj(f, out, 16 << 20)
+                os.replace(tmp, a.filter_out)
+                for p in parts:
+                    os.unlink(p)
     finally:
         for p in procs:
             if p.poll() is None:
@@ -447,7 +464,6 @@ def cmd_match_db(a):
         want_filter = bool(a.filter_out) and (n_shards == 1 or nccl)
         if a.filter_out and not want_filter:
             _die("--filter-out needs all batches: use --gpus N, or run `filter` over the match files of all shards")
-        collect = want_filter and (not nccl or rank == 0)     # who assembles 04_filter
         brank = sharding.global_batch_ranks(batches)
         rounds = [sorted(x.name for x in rnd[shard]) for rnd in plan.rounds]
         loader = _TPE(max_workers=1)                           # index loads run beside everything else
@@ -468,6 +484,9 @@ def cmd_match_db(a):
         # collapsed).  For plain FASTA with unique names that is the record list itself.
         qnames = queries = qid = rec2qid = None
         identity = False
+        # multi-GPU: with plain FASTA (identity below) every rank finalises and writes its own slice of the
+        # queries ("merge_mode" 1, parts joined by the parent); otherwise rank 0 collects everything
+        collect = want_filter
         if collect:
             with tm.span("query_names_s"):
                 qnames = qf.names()
@@ -477,11 +496,28 @@ def cmd_match_db(a):
                     rec2qid = np.array([qid[nm] for nm in qnames], dtype=np.int64)
                 else:
                     qid = {nm: i for i, nm in enumerate(qnames)} if merged_inputs else None
+        sharded_merge = bool(nccl and want_filter and identity and not a.bucket_dir)
+        if nccl and not sharded_merge:
+            collect = want_filter and rank == 0
         n_merge_queries = qf.n if identity else (len(queries) if queries is not None else 0)
+        blocks = qf.block_ranges(a.query_block_bases)
+
+        def own_range(q0, q1):
+            """Queries of block [q0, q1) whose merged lists this rank holds (phy_merged_range)."""
+            if not sharded_merge:
+                return q0, q1
+            n = q1 - q0
+            return q0 + n * rank // world, q0 + n * (rank + 1) // world
         pieces, refs_by_rank = [], {}
         if collect and merged_inputs:
             with tm.span("parse_existing_s"):
                 pieces, refs_by_rank = _parsed_pieces(merged_inputs, qid, brank, open(os.devnull, "w"))
+            if sharded_merge:                                 # keep the candidates of this rank's queries only
+                own = np.zeros(qf.n, dtype=bool)
+                for q0, q1 in blocks:
+                    lo, hi = own_range(q0, q1)
+                    own[lo:hi] = True
+                pieces = [(qs[own[qs]], cs[own[qs]]) for qs, cs in pieces]
         if nccl:                                              # rank 0 publishes the NCCL id through a file
             id_file = os.environ["PHYLIGN_NCCL_ID_FILE"]
             if rank == 0:
@@ -489,7 +525,8 @@ def cmd_match_db(a):
                     f.write(nccl_unique_id())
                 os.replace(id_file + ".tmp", id_file)
             m.nccl_init(_wait_for_file(id_file, float(os.environ.get("PHYLIGN_NCCL_ID_TIMEOUT", 300))), rank, world)
-        blocks = qf.block_ranges(a.query_block_bases)
+            m.set_option("shard_query_upload", 1)             # every worker passes the same queries
+            m.set_option("merge_mode", int(sharded_merge))
         # page-locked result buffers pay off when they are reused block after block; a single
         # (round, block) run fetches once, so plain host memory is cheaper than pinning it
         m.set_option("pinned_results", int(len(blocks) * max(1, len(plan.rounds)) > 2))
@@ -550,6 +587,9 @@ def cmd_match_db(a):
                                 q_of = q0 + np.repeat(np.arange(q1 - q0, dtype=np.int64),
                                                       np.diff(moffs.astype(np.int64)))
                                 pieces.append((q_of if identity else rec2qid[q_of], np.array(mc)))
+                            if sharded_merge:
+                                lo, hi = m.merged_range()
+                                assert (q0 + lo, q0 + hi) == own_range(q0, q1)
                         elif nccl and want_filter:
                             m.merged()                          # non-holders still take part in the fetch
                     if fut is not None:
@@ -610,7 +650,13 @@ def cmd_match_db(a):
                     direct_arrays = _merge_pieces(m, n_merge_queries, pieces, a.n)
                     direct_merged = m._merged_owner
             with tm.span("write_filter_s"):
-                if identity:                                  # flat arrays straight into the file (tmp + rename)
+                if sharded_merge:                             # this rank's slice of every block, one part each
+                    from .cobs_text import write_filter_fasta_native
+                    for bi, (q0, q1) in enumerate(blocks):
+                        lo, hi = own_range(q0, q1)
+                        write_filter_fasta_native(f"{a.filter_out}.part.{bi:06d}.{rank:04d}", direct_merged.ptr, qf,
+                                                  refs_by_rank, lo, hi)
+                elif identity:                                # flat arrays straight into the file (tmp + rename)
                     from .cobs_text import write_filter_fasta_native
                     write_filter_fasta_native(a.filter_out, direct_merged.ptr, qf, refs_by_rank)
                 else:

@@ -17,6 +17,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -147,8 +148,9 @@ extern "C" int phy_write_filter_fasta(const char* final_path, const phy_merged* 
                                       const uint64_t* hoffs, const uint32_t* name_len, const char* seqs,
                                       const uint64_t* soffs, uint32_t n_batches, const char* const* ref_names,
                                       const uint64_t* const* ref_offs, const uint32_t* ref_counts,
-                                      uint64_t* file_bytes) {
+                                      uint32_t q_begin, uint32_t q_end, uint64_t* file_bytes) {
     if (!final_path || !m || !headers || !hoffs || !name_len || !seqs || !soffs) return PHY_ERR_ARG;
+    q_end = std::min(q_end, m->n_queries);
     std::string tmp = std::string(final_path) + ".tmp." + std::to_string((long)getpid());
     int fd = ::open(tmp.c_str(), O_WRONLY | O_CREAT | O_TRUNC | O_CLOEXEC, 0644);
     if (fd < 0) {
@@ -171,7 +173,7 @@ extern "C" int phy_write_filter_fasta(const char* final_path, const phy_merged* 
     };
     auto put = [&](const char* p, size_t n) { buf.insert(buf.end(), p, p + n); };
     int rc = PHY_OK;
-    for (uint32_t q = 0; q < m->n_queries && ok; q++) {
+    for (uint32_t q = q_begin; q < q_end && ok; q++) {
         buf.push_back('>');
         put(headers + hoffs[q], name_len[q]);
         buf.push_back(' ');
