@@ -692,6 +692,7 @@ def run_match_db(workdir, tag, fasta, n_gpus, bases, hbm_budget_gb=0):
            "breakdown_s": dict(ph, process_start_and_exit=round(wall - timing["total_s"], 3), total_in_process=round(timing["total_s"], 3)),
            "host_s_outside_gpu_and_load": round(host_s, 3), "gpu_match_s": round(ph.get("gpu_match_s", 0.0), 3),
            "writer": timing["writer"], "direct_device_merge": timing.get("direct_device_merge"),
+           "rounds": timing.get("rounds"), "overlap_rounds": timing.get("overlap_rounds"),
            "gpu_phase_ms_hash_gather_merge": timing.get("gpu_phase_ms_hash_gather_merge"),
            "inputs": {"index_files": len(files), "index_bytes": sum(os.path.getsize(os.path.join(workdir, "cobs", f))
                                                                      for f in os.listdir(os.path.join(workdir, "cobs"))),
@@ -842,6 +843,8 @@ def run_ours(args, w, rank, world, local_rank):
                     f.write("\n".join(all_names) + "\n")
                 write_fasta(os.path.join(workdir, "reads.fa"), raw, w["n_reads"], L)
                 write_fasta(os.path.join(workdir, "reads150.fa"), raw150, w150["n_reads"], SHORT_READ_LEN)
+            if world > 1:
+                m.nccl_finalize()           # collective, orderly end of the communicator
             m.close()                       # the CLI needs the HBM
             m = None
             exp_all = dist.gather(exp_files)
@@ -860,6 +863,19 @@ def run_ours(args, w, rank, world, local_rank):
                                          f"{len(bad)} match files, 04_filter equal: {got[1] == exp_fa}")
                     f150, _ = run_match_db(workdir, "150", os.path.join(workdir, "reads150.fa"), world, w150["bases"])
                     secondary["reads150"]["e2e_files"] = f150
+                    # HBM-overflow streaming: the same run with the per-GPU budget capped so that the
+                    # batches need several resident rounds; round r+1 loads while round r is matched
+                    per_gpu = sum(b["signature_size"] * 512 for b in w["batches"]) / world
+                    cap_gb = max(8.0, 0.55 * per_gpu / 1e9 + 4.0)
+                    fcap, gotc = run_match_db(workdir, "capped", os.path.join(workdir, "reads.fa"), world, w["bases"],
+                                              hbm_budget_gb=cap_gb)
+                    if gotc is not None:
+                        fcap["files_equal_device_results"] = bool(gotc[0] == want and gotc[1] == exp_fa)
+                        fcap["hbm_budget_gb_per_gpu"] = round(cap_gb, 1)
+                        fcap["wall_vs_fully_resident"] = round(fcap["wall_s"] / e2e_files["wall_s"], 3)
+                        if not fcap["files_equal_device_results"]:
+                            raise SystemExit("capped-budget match-db run produced different files")
+                    secondary["streaming_capped_hbm"] = fcap
             dist.barrier()
         finally:
             dist.barrier()
@@ -869,11 +885,14 @@ def run_ours(args, w, rank, world, local_rank):
     # ---- at 8 GPUs: BASELINE configs[3], the full 661k-shaped database
     if world == 8 and w["name"] == "reads1k" and not args.no_db661k:
         if m is not None:
+            m.nccl_finalize()
             m.close()
             m = None
         sec = secondary_db661k(args, dist, rank, world, local_rank)
         if rank == 0:
             secondary.update(sec)
+    if m is not None and world > 1:
+        m.nccl_finalize()
     if rank != 0:
         if m is not None:
             m.close()
@@ -1009,6 +1028,7 @@ def secondary_db661k(args, dist, rank, world, local_rank):
     del res0, mo0, mc0
     m.set_option("prune", 1)
     local_row_bytes = sum((b["n_docs"] + 7) // 8 for b in placement[rank])
+    m.nccl_finalize()
     m.close()
     dist.barrier()
     if rank != 0:

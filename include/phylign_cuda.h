@@ -259,6 +259,9 @@ int phy_write_match_blocks(const phy_results* r, const phy_mfile_job* jobs, uint
 #define PHY_NCCL_ID_BYTES 128
 int phy_nccl_unique_id(void* id_out /* PHY_NCCL_ID_BYTES */);
 int phy_nccl_init(phy_ctx* ctx, const void* id, int rank, int n_ranks);
+/* collective end of the communicator (ncclCommFinalize + ncclCommDestroy): all ranks call it at the same
+ * point.  A context destroyed without it aborts its communicator locally (never blocks on peers). */
+int phy_nccl_finalize(phy_ctx* ctx);
 
 /* -------------------------------------------------------------------- timing
  * CUDA-event timer on the stream every kernel of this ctx is launched on. */

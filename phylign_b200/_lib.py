@@ -141,6 +141,7 @@ PROTOTYPES = {
                                         C.c_void_p, C.c_int, C.c_int, C.POINTER(WriteStats)]),
     "phy_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "phy_nccl_init": (C.c_int, [_P, C.c_void_p, C.c_int, C.c_int]),
+    "phy_nccl_finalize": (C.c_int, [_P]),
     "phy_timer_start": (C.c_int, [_P]),
     "phy_timer_stop": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "phy_sync": (C.c_int, [_P]),

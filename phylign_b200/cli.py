@@ -671,6 +671,8 @@ def cmd_match_db(a):
                     for b in batches:
                         _atomic_write(os.path.join(a.bucket_dir, f"{b}____{qfile}.candidates.tsv"),
                                       format_bucket_tsv(buckets.get(brank[b], [])).encode(), gz=False)
+        if nccl:
+            m.nccl_finalize()    # every worker gets here after the same number of collectives
         m.release_at_exit()      # HBM goes back with the process: no cudaFree per index on the way out
         if a.timing_json and (not nccl or rank == 0):
             w = {k: sum(d[k] for d in wstats) for k in (wstats[0] if wstats else {}) if k != "threads"}

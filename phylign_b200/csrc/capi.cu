@@ -149,8 +149,7 @@ extern "C" void phy_ctx_destroy(phy_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     phy_loader_destroy(ctx);
-    // the NCCL communicator is left to process exit: ncclCommDestroy blocks for tens of seconds when
-    // the peer ranks tear down at different times (measured), and one ctx lives as long as its process
+    phy_nccl_shutdown(ctx);  // no-op after phy_nccl_finalize; otherwise a local, non-blocking abort
     for (auto& ix : ctx->idx) {
         if (ix.rows_mut) cudaFree(ix.rows_mut);
         if (ix.ref_rank_mut) cudaFree(ix.ref_rank_mut);

@@ -23,6 +23,8 @@ struct NcclApi {
     ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*CommFinalize)(ncclComm_t) = nullptr;
+    ncclResult_t (*CommAbort)(ncclComm_t) = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
@@ -53,6 +55,8 @@ int load_nccl(phy_ctx* ctx) {
     LOAD(GetUniqueId, "ncclGetUniqueId")
     LOAD(CommInitRank, "ncclCommInitRank")
     LOAD(CommDestroy, "ncclCommDestroy")
+    LOAD(CommFinalize, "ncclCommFinalize")
+    LOAD(CommAbort, "ncclCommAbort")
     LOAD(AllGather, "ncclAllGather")
     LOAD(Send, "ncclSend")
     LOAD(Recv, "ncclRecv")
@@ -185,11 +189,37 @@ extern "C" int phy_nccl_init(phy_ctx* ctx, const void* id, int rank, int n_ranks
     ctx->nccl_comm = comm;
     ctx->rank = rank;
     ctx->n_ranks = n_ranks;
+    // first collective now: NCCL sets up its peer connections lazily (hundreds of ms), and callers
+    // run the init beside their index load -- not inside the first query upload or merge
+    void* d = nullptr;
+    PHY_TRY(phy_ws_alloc(ctx, &d, 256 * (size_t)n_ranks));
+    PHY_NCCL(ctx, g_nccl.AllGather((const uint8_t*)d + 256 * (size_t)rank, d, 256, ncclChar, comm, ctx->stream));
+    PHY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    phy_ws_free(ctx, d);
     return PHY_OK;
 }
 
+// Collective, orderly end of the communicator: every rank calls it at the same point of the job
+// (ncclCommFinalize flushes outstanding work, ncclCommDestroy then only frees local resources).
+extern "C" int phy_nccl_finalize(phy_ctx* ctx) {
+    if (!ctx) return PHY_ERR_ARG;
+    if (!ctx->nccl_comm) return PHY_OK;
+    PHY_CUDA(ctx, cudaSetDevice(ctx->device));
+    PHY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
+    ctx->nccl_comm = nullptr;
+    ctx->n_ranks = 1;
+    ctx->rank = 0;
+    PHY_NCCL(ctx, g_nccl.CommFinalize(comm));
+    PHY_NCCL(ctx, g_nccl.CommDestroy(comm));
+    return PHY_OK;
+}
+
+// Context teardown without phy_nccl_finalize (a rank leaving on an error path, ranks ending at
+// different times): ncclCommAbort releases the communicator locally and never waits for peers --
+// ncclCommDestroy alone blocked for tens of seconds in that situation (measured in round 1).
 void phy_nccl_shutdown(phy_ctx* ctx) {
-    if (ctx->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)ctx->nccl_comm);
+    if (ctx->nccl_comm && g_nccl.CommAbort) g_nccl.CommAbort((ncclComm_t)ctx->nccl_comm);
     ctx->nccl_comm = nullptr;
     ctx->n_ranks = 1;
     ctx->rank = 0;

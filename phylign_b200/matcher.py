@@ -527,6 +527,14 @@ class Matcher:
         self._ck(self._L.phy_nccl_init(self._ctx, uid, rank, n_ranks))
 
 
+def _nccl_finalize(self):
+    """Collective: every rank of the job calls it at the same point (orderly communicator shutdown)."""
+    self._ck(self._L.phy_nccl_finalize(self._ctx))
+
+
+Matcher.nccl_finalize = _nccl_finalize
+
+
 def nccl_unique_id() -> bytes:
     buf = C.create_string_buffer(_lib.NCCL_ID_BYTES)
     _lib.check(_lib.load().phy_nccl_unique_id(buf))
