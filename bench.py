@@ -883,7 +883,7 @@ def run_ours(args, w, rank, world, local_rank):
                 shutil.rmtree(workdir, ignore_errors=True)
 
     # ---- at 8 GPUs: BASELINE configs[3], the full 661k-shaped database
-    if world == 8 and w["name"] == "reads1k" and not args.no_db661k:
+    if (world == 8 or (args.force_db661k and world > 1)) and w["name"] == "reads1k" and not args.no_db661k:
         if m is not None:
             m.nccl_finalize()
             m.close()
@@ -1069,6 +1069,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e-files", action="store_true", help="skip the files-in -> files-out run of match-db")
     ap.add_argument("--no-db661k", action="store_true", help="at --gpus 8: skip secondary.db661k")
+    ap.add_argument("--force-db661k", action="store_true", help=argparse.SUPPRESS)   # secondary.db661k at any N > 1 (tests)
     ap.add_argument("--merge-on-rank0", action="store_true",
                     help="N > 1: gather the merged lists on rank 0 and replicate the query upload (round-1 behaviour)")
     ap.add_argument("--workdir", default=None, help=argparse.SUPPRESS)

@@ -488,8 +488,7 @@ extern "C" int phy_index_set_ranks(phy_ctx* ctx, int idx_id, uint32_t batch_rank
 extern "C" int phy_index_set_active(phy_ctx* ctx, int idx_id, int active) {
     HostIndex* ix = get_index(ctx, idx_id);
     if (!ix) return PHY_ERR_ARG;
-    ix->active = active != 0;
-    ctx->have_match = ctx->have_merged = false;
+    ix->active = active != 0;  // takes effect with the next phy_match_run; fetched / fetchable results stay valid
     return PHY_OK;
 }
 
