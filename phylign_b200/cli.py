@@ -373,6 +373,11 @@ def cmd_match_db(a):
     if a.gpus > 1 and rank < 0:
         return _spawn_match_db_workers(a)
     nccl = a.gpus > 1 and rank >= 0          # worker of a multi-GPU job: candidate lists meet over NCCL
+    if nccl:                                 # the workers share the host's cores
+        a.load_workers = max(2, a.load_workers // world)
+        if not a.write_threads:
+            from .match_files import default_threads
+            a.write_threads = max(2, default_threads() // world)
     if nccl and a.shard:
         _die("--gpus and --shard are alternatives")
     with open(a.batches) as f:

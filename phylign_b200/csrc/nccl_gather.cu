@@ -4,8 +4,8 @@
 // each GPU holds a shard of the indexes and sees every query.  The only real exchange is
 // the one filter_queries.py performs across batch files
 // (/root/reference/scripts/filter_queries.py:178-185): the per-GPU top-N + ties lists are
-// gathered over NVLink to rank 0 and merged once more with the same kernel.  Correct
-// because global top-N + ties is a subset of the union of per-GPU top-N + ties.
+// exchanged over NVLink and merged once more with the same kernel.  Correct because global
+// top-N + ties is a subset of the union of per-GPU top-N + ties.
 //
 // libnccl is resolved with dlopen at phy_nccl_init time, so single-GPU users never need it
 // and the process shares whichever libnccl.so.2 is already loaded (e.g. PyTorch's).
@@ -26,10 +26,6 @@ struct NcclApi {
     ncclResult_t (*CommFinalize)(ncclComm_t) = nullptr;
     ncclResult_t (*CommAbort)(ncclComm_t) = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*GroupStart)() = nullptr;
-    ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 NcclApi g_nccl;
@@ -58,10 +54,6 @@ int load_nccl(phy_ctx* ctx) {
     LOAD(CommFinalize, "ncclCommFinalize")
     LOAD(CommAbort, "ncclCommAbort")
     LOAD(AllGather, "ncclAllGather")
-    LOAD(Send, "ncclSend")
-    LOAD(Recv, "ncclRecv")
-    LOAD(GroupStart, "ncclGroupStart")
-    LOAD(GroupEnd, "ncclGroupEnd")
     LOAD(GetErrorString, "ncclGetErrorString")
 #undef LOAD
     g_nccl.handle = h;
@@ -76,41 +68,6 @@ int load_nccl(phy_ctx* ctx) {
             return PHY_ERR_NCCL;                                                              \
         }                                                                                     \
     } while (0)
-
-// per-query candidate count over all ranks; foffs_all = [R][nq+1]
-__global__ void __launch_bounds__(256) rank_totals_kernel(const uint64_t* __restrict__ foffs_all, uint32_t n_ranks,
-                                                          uint32_t nq, uint32_t* __restrict__ totals) {
-    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= nq) return;
-    uint64_t t = 0;
-    for (uint32_t r = 0; r < n_ranks; r++) {
-        const uint64_t* f = foffs_all + (uint64_t)r * (nq + 1);
-        t += f[q + 1] - f[q];
-    }
-    totals[q] = (uint32_t)t;
-}
-
-// copy every rank's candidates of query q behind each other into the merge segments
-__global__ void __launch_bounds__(128) regroup_kernel(const uint64_t* __restrict__ foffs_all,
-                                                      const uint64_t* __restrict__ rank_base, uint32_t n_ranks,
-                                                      uint32_t nq, const phy_cand* __restrict__ recv,
-                                                      const uint64_t* __restrict__ qoffs_c,
-                                                      uint64_t* __restrict__ ckey, uint32_t* __restrict__ cval) {
-    for (uint32_t q = blockIdx.x; q < nq; q += gridDim.x) {
-        uint64_t dst = qoffs_c[q];
-        for (uint32_t r = 0; r < n_ranks; r++) {
-            const uint64_t* f = foffs_all + (uint64_t)r * (nq + 1);
-            const uint64_t src = rank_base[r] + f[q];
-            const uint32_t n = (uint32_t)(f[q + 1] - f[q]);
-            for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-                phy_cand c = recv[src + i];
-                ckey[dst + i] = ((uint64_t)(~c.score) << 32) | ((uint64_t)c.batch_rank << 20) | c.ref_rank;
-                cval[dst + i] = c.doc;
-            }
-            dst += n;
-        }
-    }
-}
 
 // ---- query-sharded merge: rank s finalises queries [qb[s], qb[s+1]) -----------------------------
 // B[r][s] = foffs_all[r][qb[s]]: where rank r's candidates for rank s's queries start
@@ -225,11 +182,13 @@ void phy_nccl_shutdown(phy_ctx* ctx) {
     ctx->rank = 0;
 }
 
-// Query-sharded variant: rank s receives every rank's candidates for ITS slice of the queries
-// (all-to-all over NVLink) and finalises those; the merged lists stay distributed over the ranks
-// (phy_merged_range tells which queries a rank holds).  The merge work and the final download then
-// shrink with the number of GPUs instead of piling up on rank 0.
-static int nccl_merge_sharded(phy_ctx* ctx, uint32_t top_n) {
+// After the local merge: the per-GPU top-N + ties lists meet over NVLink and are merged once more with
+// the same kernel.  "merge_mode" 1 (query-sharded): rank s finalises ITS slice of the queries and the
+// merged lists stay distributed over the ranks (phy_merged_range tells which queries a rank holds), so
+// the merge work and the final download shrink with the number of GPUs.  "merge_mode" 0: rank 0
+// finalises every query.
+int phy_nccl_merge(phy_ctx* ctx, uint32_t top_n) {
+    const bool sharded = ctx->merge_sharded;
     ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
     const uint32_t nq = ctx->nq, R = (uint32_t)ctx->n_ranks, me = (uint32_t)ctx->rank;
     auto qb = [&](uint32_t s) { return (uint32_t)((uint64_t)nq * s / R); };
@@ -243,22 +202,22 @@ static int nccl_merge_sharded(phy_ctx* ctx, uint32_t top_n) {
     PHY_CUDA(ctx, cudaMemcpyAsync(B.data(), d_bounds, B.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
     PHY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     auto bound = [&](uint32_t r, uint32_t s) { return B[(size_t)r * (R + 1) + s]; };
+    // Exchange: ONE padded all-gather of every rank's list (a few tens of MB in all) instead of R x R
+    // send/recv pairs -- it runs on the collective connections set up at init, whereas the first
+    // ncclSend/ncclRecv to each peer costs seconds of lazy point-to-point set-up (measured: 7.7 s for the
+    // first match pass of a fresh 8-GPU job).  Each rank then reads its query slice out of every list.
+    uint64_t maxn = 1;
+    for (uint32_t r = 0; r < R; r++) maxn = std::max<uint64_t>(maxn, bound(r, R));
     std::vector<uint64_t> base(R + 1, 0);
-    for (uint32_t r = 0; r < R; r++) base[r + 1] = base[r] + (bound(r, me + 1) - bound(r, me));
-    PHY_TRY(phy_ensure(ctx, ctx->d_recv, base[R] + 1));
-    static_assert(sizeof(phy_cand) == 16, "phy_cand is sent as 4 x uint32");
-    PHY_NCCL(ctx, g_nccl.GroupStart());
-    for (uint32_t s = 0; s < R; s++) {
-        if (s == me) continue;
-        const uint64_t n_to = bound(me, s + 1) - bound(me, s), n_from = base[s + 1] - base[s];
-        if (n_to) PHY_NCCL(ctx, g_nccl.Send(ctx->d_final.p + bound(me, s), n_to * 4, ncclUint32, (int)s, comm, ctx->stream));
-        if (n_from) PHY_NCCL(ctx, g_nccl.Recv(ctx->d_recv.p + base[s], n_from * 4, ncclUint32, (int)s, comm, ctx->stream));
-    }
-    PHY_NCCL(ctx, g_nccl.GroupEnd());
-    if (base[me + 1] > base[me])
-        PHY_CUDA(ctx, cudaMemcpyAsync(ctx->d_recv.p + base[me], ctx->d_final.p + bound(me, me),
-                                      (base[me + 1] - base[me]) * sizeof(phy_cand), cudaMemcpyDeviceToDevice, ctx->stream));
-    const uint32_t q_lo = qb(me), q_hi = qb(me + 1);
+    const uint32_t q_lo = sharded ? qb(me) : 0, q_hi = sharded ? qb(me + 1) : (me == 0 ? nq : 0);
+    for (uint32_t r = 0; r < R; r++)       // rank r's first candidate for my slice of the queries
+        base[r] = (uint64_t)r * maxn + (sharded ? bound(r, me) : 0);
+    PHY_TRY(phy_ensure(ctx, ctx->d_recv, (size_t)R * maxn + 1));
+    static_assert(sizeof(phy_cand) == 16, "phy_cand is exchanged as 4 x uint32");
+    if (bound(me, R))
+        PHY_CUDA(ctx, cudaMemcpyAsync(ctx->d_recv.p + (size_t)me * maxn, ctx->d_final.p, bound(me, R) * sizeof(phy_cand),
+                                      cudaMemcpyDeviceToDevice, ctx->stream));
+    PHY_NCCL(ctx, g_nccl.AllGather(ctx->d_recv.p + (size_t)me * maxn, ctx->d_recv.p, maxn * 4, ncclUint32, comm, ctx->stream));
     PHY_TRY(phy_ensure(ctx, ctx->d_rank_base, R + 1));
     PHY_TRY(phy_h2d(ctx, ctx->d_rank_base.p, base.data(), (R + 1) * sizeof(uint64_t)));
     PHY_TRY(phy_ensure(ctx, ctx->d_qcount, nq + 1));
@@ -280,64 +239,5 @@ static int nccl_merge_sharded(phy_ctx* ctx, uint32_t top_n) {
     }
     ctx->merged_q_lo = q_lo;
     ctx->merged_q_hi = q_hi;
-    return phy_merge_segments(ctx, top_n);
-}
-
-// After the local merge: gather every rank's (d_foffs, d_final) on rank 0 and merge again.
-int phy_nccl_merge(phy_ctx* ctx, uint32_t top_n) {
-    if (ctx->merge_sharded) return nccl_merge_sharded(ctx, top_n);
-    ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
-    const uint32_t nq = ctx->nq, R = (uint32_t)ctx->n_ranks;
-    ctx->merged_q_lo = 0;
-    ctx->merged_q_hi = ctx->rank == 0 ? nq : 0;
-    // (1) every rank learns every rank's per-query offsets (tiny: R x (nq+1) x 8 B)
-    DevBuf<uint64_t>& all = ctx->d_foffs_all;
-    PHY_TRY(phy_ensure(ctx, all, (size_t)R * (nq + 1)));
-    PHY_NCCL(ctx, g_nccl.AllGather(ctx->d_foffs.p, all.p, nq + 1, ncclUint64, comm, ctx->stream));
-    std::vector<uint64_t> totals(R), base(R + 1, 0);
-    for (uint32_t r = 0; r < R; r++)
-        PHY_CUDA(ctx, cudaMemcpyAsync(&totals[r], all.p + (size_t)r * (nq + 1) + nq, sizeof(uint64_t),
-                                      cudaMemcpyDeviceToHost, ctx->stream));
-    PHY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    for (uint32_t r = 0; r < R; r++) base[r + 1] = base[r] + totals[r];
-    // (2) candidate lists -> rank 0 over NVLink
-    static_assert(sizeof(phy_cand) == 16, "phy_cand is sent as 4 x uint32");
-    if (ctx->rank == 0) {
-        PHY_TRY(phy_ensure(ctx, ctx->d_recv, base[R] + 1));
-        if (totals[0])
-            PHY_CUDA(ctx, cudaMemcpyAsync(ctx->d_recv.p, ctx->d_final.p, totals[0] * sizeof(phy_cand),
-                                          cudaMemcpyDeviceToDevice, ctx->stream));
-        PHY_NCCL(ctx, g_nccl.GroupStart());
-        for (uint32_t r = 1; r < R; r++)
-            if (totals[r])
-                PHY_NCCL(ctx, g_nccl.Recv(ctx->d_recv.p + base[r], totals[r] * 4, ncclUint32, (int)r, comm, ctx->stream));
-        PHY_NCCL(ctx, g_nccl.GroupEnd());
-    } else {
-        if (totals[ctx->rank])
-            PHY_NCCL(ctx, g_nccl.Send(ctx->d_final.p, totals[ctx->rank] * 4, ncclUint32, 0, comm, ctx->stream));
-        ctx->n_final = 0;
-        PHY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        return PHY_OK;
-    }
-    // (3) rank 0: regroup by query and run the same sort + cut kernel over the union
-    PHY_TRY(phy_ensure(ctx, ctx->d_rank_base, R + 1));
-    PHY_TRY(phy_h2d(ctx, ctx->d_rank_base.p, base.data(), (R + 1) * sizeof(uint64_t)));
-    PHY_TRY(phy_ensure(ctx, ctx->d_qcount, nq + 1));
-    if (nq) {
-        rank_totals_kernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(all.p, R, nq, ctx->d_qcount.p);
-        ctx->launches++;
-    }
-    uint64_t total = 0;
-    PHY_TRY(phy_ensure(ctx, ctx->d_qoffs_c, nq + 2));
-    PHY_TRY(phy_exscan(ctx, ctx->d_qcount.p, nq, ctx->d_qoffs_c.p, &total));
-    PHY_TRY(phy_ensure(ctx, ctx->d_ckey, total + 1));
-    PHY_TRY(phy_ensure(ctx, ctx->d_cval, total + 1));
-    if (nq && total) {
-        unsigned blocks = (unsigned)std::min<uint64_t>(nq, 148ull * 32);
-        regroup_kernel<<<blocks, 128, 0, ctx->stream>>>(all.p, ctx->d_rank_base.p, R, nq, ctx->d_recv.p,
-                                                       ctx->d_qoffs_c.p, ctx->d_ckey.p, ctx->d_cval.p);
-        ctx->launches++;
-        PHY_CUDA(ctx, cudaGetLastError());
-    }
     return phy_merge_segments(ctx, top_n);
 }
