@@ -99,6 +99,12 @@ void phy_host_free(void* p);
  * offs[nq+1]: start of each query in seq_concat.  Copies host -> HBM. */
 int phy_queries_set(phy_ctx* ctx, const char* seq_concat, const uint64_t* offs, uint32_t nq);
 
+/* Query preparation of rule fix_query (Snakefile:314-332, `seqtk seq -A -U -C | awk gsub(/[^ACGT]/,"A")`)
+ * for the bases, on the device: upper-case, every letter outside ACGT becomes 'A'.  In place over n bytes
+ * of a host buffer (upload, one kernel, download).  With the option "sanitize_queries" 1, phy_queries_set
+ * applies the same transform to the uploaded queries instead of rejecting such letters. */
+int phy_fix_bases(phy_ctx* ctx, char* bases, uint64_t n);
+
 /* ----------------------------------------------------------------------- match */
 typedef struct phy_match_params {
     double threshold;     /* cobs -t : doc reported iff score >= threshold*K */
@@ -282,7 +288,8 @@ int phy_ctx_budget(phy_ctx* ctx, uint64_t* budget, uint64_t* used);
  * "pinned_results" 0|1 (phy_results / phy_merged in page-locked memory from a reuse pool, default 1;
  * 0 = plain host memory, cheaper for a single fetch), "merge_mode" 0|1 (multi-GPU: merged lists on rank 0 |
  * one slice of the queries per rank, see phy_merged_range), "shard_query_upload" 0|1 (multi-GPU, all ranks
- * pass identical queries: each uploads 1/R of the bases, an NCCL all-gather completes them) */
+ * pass identical queries: each uploads 1/R of the bases, an NCCL all-gather completes them),
+ * "sanitize_queries" 0|1 (see phy_fix_bases) */
 int phy_ctx_set_option(phy_ctx* ctx, const char* name, int64_t value);
 /* write a buffer larger than L2 (bench hygiene between timed iterations) */
 int phy_flush_l2(phy_ctx* ctx);

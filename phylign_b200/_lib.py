@@ -112,6 +112,7 @@ PROTOTYPES = {
     "phy_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "phy_host_free": (None, [C.c_void_p]),
     "phy_queries_set": (C.c_int, [_P, C.c_void_p, C.c_void_p, C.c_uint32]),
+    "phy_fix_bases": (C.c_int, [_P, C.c_void_p, C.c_uint64]),
     "phy_match_run": (C.c_int, [_P, C.POINTER(MatchParams), C.c_uint32]),
     "phy_results_fetch": (C.c_int, [_P, C.POINTER(C.POINTER(Results))]),
     "phy_results_free": (None, [C.POINTER(Results)]),

@@ -225,6 +225,25 @@ def cmd_filter(a):
     sys.stdout.flush()
 
 
+def cmd_fix_query(a):
+    """rules fix_query + concatenate_queries (Snakefile:314-352): FASTA/FASTQ in, one-line FASTA out,
+    names without comments, bases upper-case ACGT (everything else -> A)."""
+    if a.device is None:
+        sys.stdout.write("".join(fasta.fix_query_file(p) for p in a.inputs))
+        return
+    from .matcher import Matcher
+    recs = [r for p in a.inputs for r in fasta.read_fastx(p)]
+    cat = np.frombuffer(bytearray("".join(s for _, s in recs).encode()), dtype=np.uint8)
+    with Matcher(a.device) as m:
+        m.fix_bases(cat)
+    out, pos = [], 0
+    fixed = cat.tobytes().decode()
+    for name, s in recs:
+        out.append(f">{name}\n{fixed[pos:pos + len(s)]}\n")
+        pos += len(s)
+    sys.stdout.write("".join(out))
+
+
 # ------------------------------------------------------------------------------------ whole database
 def _atomic_write(path, data: bytes, gz: bool):
     tmp = f"{path}.tmp.{os.getpid()}"
@@ -506,6 +525,9 @@ def cmd_match_db(a):
             collect = want_filter and rank == 0
         n_merge_queries = qf.n if identity else (len(queries) if queries is not None else 0)
         blocks = qf.block_ranges(a.query_block_bases)
+        if a.sanitize_queries:      # raw queries: rule fix_query's base transform on the device, once; the
+            with tm.span("sanitize_queries_s"):   # 04_filter FASTA then carries the sanitised sequences too
+                m.fix_bases(qf.seqs[:qf.total_bases])
 
         def own_range(q0, q1):
             """Queries of block [q0, q1) whose merged lists this rank holds (phy_merged_range)."""
@@ -749,7 +771,9 @@ def build_parser():
 
     fq = sub.add_parser("fix-query", help="seqtk seq -A -U -C | awk non-ACGT->A (Snakefile:326-332), all inputs concatenated")
     fq.add_argument("inputs", nargs="+")
-    fq.set_defaults(fn=lambda a: sys.stdout.write("".join(fasta.fix_query_file(p) for p in a.inputs)))
+    fq.add_argument("--device", type=int, default=None,
+                    help="run the base transform on this GPU (phy_fix_bases) instead of the host table")
+    fq.set_defaults(fn=cmd_fix_query)
 
     d = sub.add_parser("match-db")
     d.add_argument("--cobs-dir", required=True)
@@ -794,6 +818,9 @@ def build_parser():
     d.add_argument("--benchmark-dir", default=None,
                    help="write logs/benchmarks/run_cobs-style {batch}____{qfile}.txt files (scripts/benchmark.py format)")
     d.add_argument("--timing-json", default=None, help="write the wall-clock breakdown of the run here")
+    d.add_argument("--sanitize-queries", action="store_true",
+                   help="the query FASTA has not gone through rule fix_query: upper-case its bases and turn every "
+                        "letter outside ACGT into A on the GPU before matching (Snakefile:326-332)")
     d.set_defaults(fn=cmd_match_db)
     return ap
 

@@ -579,7 +579,21 @@ extern "C" int phy_queries_set(phy_ctx* ctx, const char* seq_concat, const uint6
     if (offs[0] != 0)
         for (auto& o : ctx->h_qoffs) o -= offs[0];
     PHY_TRY(phy_h2d(ctx, ctx->d_qoffs.p, ctx->h_qoffs.data(), (nq + 1) * sizeof(uint64_t)));
+    if (ctx->sanitize_queries) PHY_TRY(phy_launch_fix_bases(ctx, (uint8_t*)ctx->d_seq.p, ctx->total_bases));
     return PHY_OK;
+}
+
+extern "C" int phy_fix_bases(phy_ctx* ctx, char* bases, uint64_t n) {
+    if (!ctx || (!bases && n)) return PHY_ERR_ARG;
+    PHY_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevBuf<char> tmp;
+    PHY_TRY(phy_ensure(ctx, tmp, n + 64));
+    int rc = phy_h2d(ctx, tmp.p, bases, n);
+    if (rc == PHY_OK) rc = phy_launch_fix_bases(ctx, (uint8_t*)tmp.p, n);
+    if (rc == PHY_OK) rc = phy_d2h(ctx, bases, tmp.p, n);
+    cudaStreamSynchronize(ctx->stream);
+    phy_release(ctx, tmp);
+    return rc;
 }
 
 // k-mer offset tables + hashes for the term size / canonical flag of the resident indexes
@@ -881,6 +895,7 @@ extern "C" int phy_ctx_set_option(phy_ctx* ctx, const char* name, int64_t value)
     else if (!strcmp(name, "pinned_results")) ctx->pinned_results = value != 0;
     else if (!strcmp(name, "merge_mode") && (value == 0 || value == 1)) ctx->merge_sharded = value == 1;
     else if (!strcmp(name, "shard_query_upload")) ctx->shard_query_upload = value != 0;
+    else if (!strcmp(name, "sanitize_queries")) ctx->sanitize_queries = value != 0;
     else {
         phy_set_error(ctx, "unknown option %s=%lld", name, (long long)value);
         return PHY_ERR_ARG;

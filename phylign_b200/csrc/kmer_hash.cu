@@ -5,6 +5,8 @@
 //   hash[j][g] = XXH64(canonical ASCII k-mer g, k, seed=j)
 // The hash is index independent; `% signature_size` happens in the gather kernel.
 // One thread per query k-mer; integer only; ~0.3% of the step time.
+#include <algorithm>
+
 #include "phy_internal.cuh"
 
 namespace {
@@ -182,7 +184,41 @@ __global__ void __launch_bounds__(256) kmer_hash31_roll_kernel(
     if (bad) report_bad(err, q);
 }
 
+// rule fix_query on the bases (Snakefile:326-332: `seqtk seq -U` + awk gsub(/[^ACGT]/,"A")): 16 bytes
+// per thread, upper-case by clearing bit 5, everything that is not then A/C/G/T becomes 'A'
+__device__ __forceinline__ uint32_t fix4(uint32_t w) {
+    uint32_t out = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        uint32_t c = ((w >> (8 * i)) & 0xFFu) & 0xDFu;
+        if (c != 'A' && c != 'C' && c != 'G' && c != 'T') c = 'A';
+        out |= c << (8 * i);
+    }
+    return out;
+}
+__global__ void __launch_bounds__(256) fix_bases_kernel(uint8_t* __restrict__ p, uint64_t n) {
+    const uint64_t n16 = n / 16;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint4 v = reinterpret_cast<uint4*>(p)[i];
+        v.x = fix4(v.x); v.y = fix4(v.y); v.z = fix4(v.z); v.w = fix4(v.w);
+        reinterpret_cast<uint4*>(p)[i] = v;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 15)) {
+        uint32_t c = p[n16 * 16 + threadIdx.x] & 0xDFu;
+        p[n16 * 16 + threadIdx.x] = (c != 'A' && c != 'C' && c != 'G' && c != 'T') ? 'A' : (uint8_t)c;
+    }
+}
+
 }  // namespace
+
+int phy_launch_fix_bases(phy_ctx* ctx, uint8_t* d_bases, uint64_t n) {
+    if (n == 0) return PHY_OK;
+    unsigned blocks = (unsigned)std::min<uint64_t>((n / 16 + 255) / 256 + 1, 148ull * 16);
+    fix_bases_kernel<<<blocks, 256, 0, ctx->stream>>>(d_bases, n);
+    ctx->launches++;
+    PHY_CUDA(ctx, cudaGetLastError());
+    return PHY_OK;
+}
 
 int phy_launch_hash(phy_ctx* ctx) {
     if (ctx->total_kmers == 0) {

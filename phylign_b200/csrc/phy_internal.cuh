@@ -60,6 +60,7 @@ struct HostIndex {
 struct phy_ctx {
     int device = 0, n_sm = 148;
     bool prune = true;    // PHY_NO_PRUNE=1 switches the exact threshold pruning of the ring kernel off
+    bool sanitize_queries = false;  // phy_queries_set applies rule fix_query's base transform on the device
     bool pinned_results = true;  // phy_results / phy_merged blocks from the page-locked pool
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_ph[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -182,6 +183,7 @@ int phy_d2h(phy_ctx* ctx, void* dst, const void* src, size_t bytes);
 
 // ---- kernels' host launchers (one per .cu) -----------------------------------------
 int phy_launch_hash(phy_ctx* ctx);
+int phy_launch_fix_bases(phy_ctx* ctx, uint8_t* d_bases, uint64_t n);
 int phy_launch_gather(phy_ctx* ctx, const phy_match_params* p);
 int phy_launch_scores(phy_ctx* ctx, int idx_id, uint32_t* d_out_scores);
 int phy_launch_sort_units(phy_ctx* ctx);

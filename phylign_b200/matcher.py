@@ -415,6 +415,14 @@ class Matcher:
         self._nq = nq
         self._ck(self._L.phy_queries_set(self._ctx, addr(cat), addr(offs), nq))
 
+    def fix_bases(self, bases):
+        """rule fix_query's base transform on the device, in place: `bases` = writable uint8 numpy array
+        (or bytearray) of sequence letters; upper-case, non-ACGT -> 'A' (Snakefile:326-332)."""
+        arr = np.frombuffer(bases, dtype=np.uint8) if not isinstance(bases, np.ndarray) else bases
+        if arr.size:
+            self._ck(self._L.phy_fix_bases(self._ctx, arr.ctypes.data, arr.size))
+        return bases
+
     # ------------------------------------------------------------------ match
     def match_run(self, threshold: float, top_n: int = 0, floor_mode: bool = False, merge_top_n: int = 0):
         p = _lib.MatchParams(float(threshold), int(top_n), int(bool(floor_mode)))

@@ -191,3 +191,42 @@ def test_query_blocks_do_not_change_the_output(tmp_path):
     for b in H.GOLDEN_BATCHES:
         assert gzip.open(mdir / f"{b}____queries.gz", "rt").read() == H.golden_match_text(b, 3)
     assert out.read_text() == H.golden_filter_fa(3)
+
+
+def test_query_prep_on_device_equals_snakefile_rule(tmp_path):
+    """phy_fix_bases / `fix-query --device` / `match-db --sanitize-queries` == rule fix_query
+    (Snakefile:326-332: seqtk seq -A -U -C | awk gsub(/[^ACGT]/,"A")) as restated on the host."""
+    import numpy as np
+    from phylign_b200.fasta import fix_query_seq
+    from phylign_b200.matcher import Matcher
+    raw = bytes(range(256)) * 9 + b"acgtnNRYKMswbdhv-*ACGT" * 41 + b"x"           # every byte value, odd length
+    with Matcher(0) as m:
+        arr = np.frombuffer(bytearray(raw), dtype=np.uint8)
+        m.fix_bases(arr)
+        assert arr.tobytes().decode("latin1") == fix_query_seq(raw.decode("latin1").encode("latin1"))
+        assert set(arr.tobytes()) <= set(b"ACGT")
+    fq = tmp_path / "r.fq"
+    fq.write_text("@r1 some comment\nacgtnACGT\n+\nIIIIIIIII\n@r2\nGGNN\n+\nIIII\n")
+    fa = tmp_path / "g.fa"
+    fa.write_text(">g1 desc\nACGT\nryk\n>g2\nTTTT\n")
+    want = _run([sys.executable, "-m", "phylign_b200.cli", "fix-query", str(fq), str(fa)])
+    got = _run([sys.executable, "-m", "phylign_b200.cli", "fix-query", "--device", "0", str(fq), str(fa)])
+    assert want.returncode == 0 and got.returncode == 0, got.stderr
+    assert got.stdout == want.stdout == ">r1\nACGTAACGT\n>r2\nGGAA\n>g1\nACGTAAA\n>g2\nTTTT\n"
+    # raw (lower-case, N-containing) queries through match-db --sanitize-queries == sanitised queries through match-db
+    recs = H.read_fasta(os.path.join(H.GOLDEN, "queries.fa"))
+    dirty = tmp_path / "dirty.fa"
+    dirty.write_text("".join(f">{h}\n{s.lower() if i % 2 else s}\n" for i, (h, s) in enumerate(recs)))
+    batches = tmp_path / "batches.txt"
+    batches.write_text("\n".join(H.GOLDEN_BATCHES) + "\n")
+    r = _run([sys.executable, "-m", "phylign_b200.cli", "match-db", "--cobs-dir", H.GOLDEN, "--batches", str(batches),
+              "-q", str(dirty), "--qfile", "queries", "--match-dir", str(tmp_path / "m"), "--filter-out",
+              str(tmp_path / "f.fa"), "-t", "0.7", "-n", "3", "--sanitize-queries"])
+    assert r.returncode == 0, r.stderr
+    for b in H.GOLDEN_BATCHES:
+        assert gzip.open(tmp_path / "m" / f"{b}____queries.gz", "rt").read() == H.golden_match_text(b, 3)
+    assert (tmp_path / "f.fa").read_text() == H.golden_filter_fa(3)
+    # without the flag the dirty file is rejected (cobs aborts on such letters too)
+    r = _run([sys.executable, "-m", "phylign_b200.cli", "match-db", "--cobs-dir", H.GOLDEN, "--batches", str(batches),
+              "-q", str(dirty), "--qfile", "queries", "--match-dir", str(tmp_path / "m2"), "-t", "0.7", "-n", "3"])
+    assert r.returncode != 0 and "ACGT" in r.stderr
