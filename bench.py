@@ -637,6 +637,37 @@ def e2e_steps(dist, m, pin_raw, pin_offs, raw_len, offs_bytes, steps, warmup, sh
     return e2e_s, h2d, d2h, [round(float(x) * 1e3 / steps, 2) for x in parts], res, moffs, mcands
 
 
+def write_index_files(m, ids, outdir, n_bufs=4):
+    """The resident indexes as {batch}.cobs_classic files (set-up of the files-in -> files-out run):
+    downloads go through a few page-locked buffers, the file writes run on threads behind them."""
+    from concurrent.futures import ThreadPoolExecutor
+    from phylign_b200.matcher import PinnedBuffer
+    if not ids:
+        return
+    size = max(m.indexes[i].header.body_size for i in ids.values())
+    bufs = [PinnedBuffer(size) for _ in range(n_bufs)]
+    pending = [None] * n_bufs
+
+    def write(path, header, buf, n):
+        tmp = f"{path}.tmp.{os.getpid()}"
+        with open(tmp, "wb") as f:
+            f.write(header)
+            f.write(memoryview(buf.array)[:n])
+        os.replace(tmp, path)
+
+    with ThreadPoolExecutor(max_workers=n_bufs) as ex:
+        for k, (name, idx) in enumerate(ids.items()):
+            b = k % n_bufs
+            if pending[b] is not None:
+                pending[b].result()
+            n = m.download_index_into(idx, bufs[b])
+            pending[b] = ex.submit(write, os.path.join(outdir, f"{name}.cobs_classic"),
+                                   m.indexes[idx].header.to_bytes(), bufs[b], n)
+        for p in pending:
+            if p is not None:
+                p.result()
+
+
 def expected_file_digests(m, records, res, mowner, names_in_rank_order, refs_by_rank):
     """sha256 of what match-db must leave on disk for this rank's indexes (decompressed text) and of the
     04_filter FASTA, formatted in-process from the device results."""
@@ -832,12 +863,9 @@ def run_ours(args, w, rank, world, local_rank):
         workdir = dist.bcast(shm_dir("phylign_bench_") if rank == 0 else None)
         try:
             os.makedirs(os.path.join(workdir, "cobs"), exist_ok=True)
-            buf = PinnedBuffer(max(m.indexes[i].header.body_size for i in m.indexes)) if m.indexes else None
             t_w = time.perf_counter()
-            for name, idx in ids.items():
-                m.write_index_file(idx, os.path.join(workdir, "cobs", f"{name}.cobs_classic"), buf)
+            write_index_files(m, ids, os.path.join(workdir, "cobs"))
             t_w = time.perf_counter() - t_w
-            del buf
             if rank == 0:
                 with open(os.path.join(workdir, "batches.txt"), "w") as f:
                     f.write("\n".join(all_names) + "\n")
