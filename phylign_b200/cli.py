@@ -102,6 +102,8 @@ def cmd_cobs_query(a):
     from .matcher import Matcher
     records = fasta.read_cobs_records(a.f)
     with Matcher(a.device) as m:
+        if getattr(a, "sanitize_queries", False):
+            m.set_option("sanitize_queries", 1)
         idx = m.load_index(a.i, batch="index")
         hdr = m.indexes[idx].header
         if a.index_sizes is not None and a.index_sizes != hdr.header_size + hdr.body_size:
@@ -737,6 +739,10 @@ def build_parser():
     q.add_argument("--query-block-bases", type=int, default=2 * 10 ** 9,
                    help="process the queries in blocks of at most this many bases (HBM for the hashes)")
     q.add_argument("--server", default=None, help="socket of a resident `serve` process (or $PHYLIGN_SERVER)")
+    q.add_argument("--sanitize-queries", action="store_true",
+                   help="queries must be upper-case ACGT (the contract of intermediate/01_queries_merged, "
+                        "Snakefile:326-332); any other letter ends the run with an error, like a cobs abort.  With this "
+                        "flag the bases are upper-cased and every other letter becomes A on the GPU first")
     q.set_defaults(fn=cmd_cobs_query)
 
     r = sub.add_parser("run-cobs-streaming")
@@ -748,7 +754,7 @@ def build_parser():
     r.add_argument("--device", type=int, default=0)
     r.set_defaults(fn=lambda a: cmd_cobs_query(argparse.Namespace(
         t=a.kmer_thres, T=0, i=a.cobs_index_xz, index_sizes=a.uncompressed_size, f=a.query, top_n=0,
-        floor=False, device=a.device, query_block_bases=2 * 10 ** 9)))
+        floor=False, device=a.device, query_block_bases=2 * 10 ** 9, sanitize_queries=False)))
 
     sv = sub.add_parser("serve", help="keep indexes resident in HBM and answer `cobs query --server` requests")
     sv.add_argument("--socket", required=True)
