@@ -1069,6 +1069,9 @@ def secondary_db661k(args, dist, rank, world, local_rank):
         return {}
     if dg != dg0:
         raise SystemExit(f"db661k: result_digest differs with pruning off: {dg} vs {dg0}")
+    exp = expected_digest(w, a2)
+    if exp is not None and dg != exp:
+        raise SystemExit(f"db661k: result_digest {dg} != committed expectation {exp} (profiles/expected_digests.json)")
     peak, _ = measured_peak()
     alg_local = w["n_reads"] * w["kmers_per_read"] * local_row_bytes
     return {"db661k": {"workload": config_dict(w)["workload"], "value": w["bases"] / (t["ms_per_step"] * 1e-3),
@@ -1082,7 +1085,8 @@ def secondary_db661k(args, dist, rank, world, local_rank):
                        "roofline_rank0": {"bytes_gathered": t["gathered"],
                                           "frac": t["gathered"] / (t["gather_ms"] * 1e-3) / 1e9 / peak,
                                           "unpruned_frac": alg_local / (un_ms * 1e-3) / 1e9 / peak},
-                       "result_digest": dg, "equals_unpruned_run": True}}
+                       "result_digest": dg, "equals_unpruned_run": True,
+                       "equals_committed_expectation": (dg == exp) if exp is not None else None}}
 
 
 def main():
