@@ -122,7 +122,7 @@ PROTOTYPES = {
     "phy_merged_free": (None, [C.POINTER(Merged)]),
     "phy_merged_range": (C.c_int, [_P, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "phy_merge_host": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
-    "phy_format_cobs_text": (C.c_int, [C.POINTER(Results), C.c_uint32, C.c_char_p, C.c_void_p, C.c_void_p, C.c_char_p,
+    "phy_format_cobs_text": (C.c_int, [C.POINTER(Results), C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p,
                                       C.c_void_p, C.c_uint32, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
     "phy_format_filter_fasta": (C.c_int, [C.POINTER(Merged), C.c_char_p, C.c_void_p, C.c_char_p, C.c_void_p, C.c_uint32,
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p),

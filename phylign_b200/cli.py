@@ -100,19 +100,24 @@ def cmd_cobs_query(a):
         sys.stdout.buffer.flush()
         return
     from .matcher import Matcher
-    records = fasta.read_cobs_records(a.f)
+    from .cobs_text import format_cobs_text_arrays
+    qf = fasta.QueryFile(a.f)                                # flat arrays (native reader)
     with Matcher(a.device) as m:
         if getattr(a, "sanitize_queries", False):
             m.set_option("sanitize_queries", 1)
+        m.set_option("pinned_results", 0)                    # one fetch per block: plain host memory is cheaper
         idx = m.load_index(a.i, batch="index")
         hdr = m.indexes[idx].header
         if a.index_sizes is not None and a.index_sizes != hdr.header_size + hdr.body_size:
             _die(f"--index-sizes {a.index_sizes} != header {hdr.header_size} + body {hdr.body_size}")
-        for _, block in query_blocks(records, a.query_block_bases):
-            m.set_queries(block)
+        for q0, q1 in qf.block_ranges(a.query_block_bases):
+            m.set_queries_raw(qf.seqs, qf.soffs[q0:q1 + 1])
             res = m.match(a.t, top_n=a.top_n, floor_mode=a.floor)
-            sys.stdout.buffer.write(format_cobs_text_fast(block, res, m.indexes[idx], strip_prefix=a.top_n > 0))
-    sys.stdout.buffer.flush()
+            sys.stdout.buffer.write(format_cobs_text_arrays(qf.headers, qf.hoffs[q0:q1 + 1], res, m.indexes[idx],
+                                                            strip_prefix=a.top_n > 0))
+        sys.stdout.buffer.flush()
+        m.release_at_exit()
+
 
 
 # ------------------------------------------------------------------------------------ filter

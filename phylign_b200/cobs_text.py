@@ -42,7 +42,28 @@ def format_cobs_text_fast(records, result, index, strip_prefix: bool = False, re
         index._names_cat = _cat(index.doc_names)
     ncat, noffs = index._names_cat
     out, n = C.c_void_p(), C.c_uint64()
-    _lib.check(L.phy_format_cobs_text(rp, index.idx_id, hcat, hoffs.ctypes.data, skip.ctypes.data, ncat,
+    _lib.check(L.phy_format_cobs_text(rp, index.idx_id, C.cast(C.c_char_p(hcat), C.c_void_p), hoffs.ctypes.data,
+                                      skip.ctypes.data, ncat,
+                                      noffs.ctypes.data, len(index.doc_names), int(strip_prefix),
+                                      C.byref(out), C.byref(n)))
+    try:
+        return C.string_at(out, n.value)
+    finally:
+        L.phy_text_free(out)
+
+
+def format_cobs_text_arrays(headers, hoffs, result, index, strip_prefix: bool = False) -> bytes:
+    """The cobs text of one index for a block of a fasta.QueryFile: `headers` = its uint8 header array,
+    `hoffs` = the block's slice of header offsets (nq+1).  No per-record Python objects."""
+    import ctypes as C
+    from . import _lib
+    L = _lib.load()
+    if not hasattr(index, "_names_cat"):
+        index._names_cat = _cat(index.doc_names)
+    ncat, noffs = index._names_cat
+    hoffs = np.ascontiguousarray(hoffs, dtype=np.uint64)
+    out, n = C.c_void_p(), C.c_uint64()
+    _lib.check(L.phy_format_cobs_text(result._owner.ptr, index.idx_id, headers.ctypes.data, hoffs.ctypes.data, None, ncat,
                                       noffs.ctypes.data, len(index.doc_names), int(strip_prefix),
                                       C.byref(out), C.byref(n)))
     try:

@@ -944,6 +944,7 @@ extern "C" int phy_index_insert(phy_ctx* ctx, int idx_id, const uint32_t* doc_of
     }
     PHY_CUDA(ctx, cudaSetDevice(ctx->device));
     PHY_TRY(prepare_hashes(ctx, ix->term_size, ix->canon, ix->d.num_hashes));
+    PHY_TRY(phy_check_hash_error(ctx));
     PHY_TRY(phy_ensure(ctx, ctx->d_slotq, ctx->nq + 1));
     PHY_TRY(phy_h2d(ctx, ctx->d_slotq.p, doc_of_query, (size_t)ctx->nq * sizeof(uint32_t)));
     PHY_TRY(phy_insert_kmers(ctx, *ix, ctx->d_slotq.p));

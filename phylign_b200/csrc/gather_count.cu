@@ -869,6 +869,7 @@ static int run_general(phy_ctx* ctx, const HostIndex& ix, int ipos, const std::v
 }
 
 int phy_launch_scores(phy_ctx* ctx, int idx_id, uint32_t* d_out_scores) {
+    PHY_TRY(phy_check_hash_error(ctx));
     const HostIndex& ix = ctx->idx[idx_id];
     std::vector<uint32_t> qs;
     for (uint32_t q = 0; q < ctx->nq; q++) qs.push_back(q);
@@ -1048,6 +1049,7 @@ int phy_launch_gather(phy_ctx* ctx, const phy_match_params* p) {
         PHY_CUDA(ctx, cudaMemcpyAsync(ctx->h_idx_bytes.data(), ctx->d_idx_bytes.p,
                                       ctx->idx.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
         PHY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->hash_check_pending) PHY_TRY(phy_hash_error_of(ctx, cnt[2]));  // K1's error word rode along
         ctx->gathered_bytes = 0;
         for (unsigned long long b : ctx->h_idx_bytes) ctx->gathered_bytes += b;
         if (cnt[0] <= ctx->d_hits.cap && cnt[1] <= ctx->d_units.cap) {

@@ -256,13 +256,27 @@ int phy_launch_hash(phy_ctx* ctx) {
     }
     ctx->launches++;
     PHY_CUDA(ctx, cudaGetLastError());
+    // the error word (a query with a letter outside ACGT) is read at the next point where the host
+    // waits for the stream anyway: phy_check_hash_error, or with the counters after the gather
+    ctx->hash_check_pending = true;
+    ctx->hashes_valid = true;
+    return PHY_OK;
+}
+
+int phy_hash_error_of(phy_ctx* ctx, unsigned long long word) {
+    ctx->hash_check_pending = false;
+    if (word != ~0ULL) {
+        ctx->hashes_valid = false;
+        phy_set_error(ctx, "query #%u holds a letter outside ACGT", (unsigned)(word & 0xFFFFFFFFu));
+        return PHY_ERR_QUERY;
+    }
+    return PHY_OK;
+}
+
+int phy_check_hash_error(phy_ctx* ctx) {
+    if (!ctx->hash_check_pending) return PHY_OK;
     unsigned long long e = 0;
     PHY_CUDA(ctx, cudaMemcpyAsync(&e, ctx->d_counters.p + 2, sizeof e, cudaMemcpyDeviceToHost, ctx->stream));
     PHY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (e != ~0ULL) {
-        phy_set_error(ctx, "query #%u holds a letter outside ACGT", (unsigned)(e & 0xFFFFFFFFu));
-        return PHY_ERR_QUERY;
-    }
-    ctx->hashes_valid = true;
-    return PHY_OK;
+    return phy_hash_error_of(ctx, e);
 }

@@ -98,6 +98,7 @@ struct phy_ctx {
     DevBuf<uint64_t> d_qoffs, d_koffs, d_hashes, d_ioffs;
     DevBuf<uint32_t> d_nk, d_T, d_qlist, d_class;
     bool hashes_valid = false;
+    bool hash_check_pending = false;  // K1's error word has not been read yet
 
     // match outputs (device resident until fetched)
     bool have_match = false, have_merged = false;
@@ -184,6 +185,8 @@ int phy_d2h(phy_ctx* ctx, void* dst, const void* src, size_t bytes);
 // ---- kernels' host launchers (one per .cu) -----------------------------------------
 int phy_launch_hash(phy_ctx* ctx);
 int phy_launch_fix_bases(phy_ctx* ctx, uint8_t* d_bases, uint64_t n);
+int phy_check_hash_error(phy_ctx* ctx);                          // sync + read K1's error word if pending
+int phy_hash_error_of(phy_ctx* ctx, unsigned long long word);    // interpret a word that was already copied
 int phy_launch_gather(phy_ctx* ctx, const phy_match_params* p);
 int phy_launch_scores(phy_ctx* ctx, int idx_id, uint32_t* d_out_scores);
 int phy_launch_sort_units(phy_ctx* ctx);
