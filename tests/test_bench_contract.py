@@ -51,3 +51,35 @@ def test_reference_arm_prints_the_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"] > 0
     assert "workload" in d["config"] and "model" not in d["config"]
+    # both arms word the workload identically (run-dependent facts live outside `config`)
+    w = bench.workload(ns(reads=120, read_len=150, indexes=2, docs=64, genome_len=2000))
+    assert d["config"] == bench.config_dict(w)
+    # files in -> files out: cobs_oracle | postprocess_cobs.py | gzip --fast, then filter_queries.py
+    f = d["e2e_files"]
+    assert f["value"] > 0 and f["unit"] == "bases/s"
+    assert set(f["breakdown_s"]) >= {"match_pipeline_one_batch", "filter_queries_all_batches", "stage_cobs_query_alone"}
+    assert "postprocess_cobs.py" in f["sample"] and f["outputs"]["filter_fasta_bytes"] > 0
+    assert "set-up subprocess" in d["native_so_policy"]
+
+
+def test_digest_helpers_are_placement_independent():
+    """result_digest ingredients: per-batch digests keyed by the global batch rank, merged lists joined in
+    query order from per-rank slices."""
+    import numpy as np
+    from phylign_b200.matcher import CAND_DT
+
+    class FakeDist:
+        world, rank = 2, 0
+        def gather(self, obj):
+            lo, hi, o, c = obj
+            other = (hi, hi + 2, np.array([0, 1, 3], np.int64), np.array([(5, 1, 2, 3), (4, 0, 1, 1), (4, 1, 0, 0)], CAND_DT))
+            return [other, obj]          # arrival order must not matter
+
+    class FakeM:
+        def merged_range(self):
+            return 0, 2
+
+    offs = np.array([0, 2, 3, 3, 3], np.uint64)
+    cands = np.array([(9, 0, 0, 0), (8, 0, 1, 1), (7, 1, 0, 0)], CAND_DT)
+    fo, fc = bench.full_merged(FakeDist(), FakeM(), offs, cands)
+    assert fo.tolist() == [0, 2, 3, 4, 6] and fc["score"].tolist() == [9, 8, 7, 5, 4, 4]

@@ -498,3 +498,38 @@ def test_native_filter_fasta_writer_equals_twin(tmp_path):
     want = format_filter_fasta([(f"q{q}", "ACGT" * (1 + q % 7)) for q in range(nq)], offs, ca, refs)
     assert out.read_text() == want and n == len(want)
     assert os.listdir(out.parent) == ["q.fa"]
+
+
+def test_match_db_gpus_parent_stops_when_a_worker_dies(tmp_path):
+    """`match-db --gpus N`: a worker that fails (here: no usable GPU, so every Matcher() raises) must take
+    the whole job down with a non-zero exit instead of leaving the others blocked in a collective
+    (the parent used to wait for every child in turn)."""
+    import subprocess
+    import sys
+    import time
+    batches = tmp_path / "batches.txt"
+    batches.write_text("\n".join(H.GOLDEN_BATCHES) + "\n")
+    t0 = time.time()
+    r = subprocess.run([sys.executable, "-m", "phylign_b200.cli", "match-db", "--cobs-dir", H.GOLDEN, "--batches",
+                        str(batches), "-q", os.path.join(H.GOLDEN, "queries.fa"), "--match-dir", str(tmp_path / "m"),
+                        "--filter-out", str(tmp_path / "f.fa"), "--gpus", "2"], capture_output=True, text=True,
+                       cwd=ROOT, env=dict(os.environ, PYTHONPATH=ROOT, CUDA_VISIBLE_DEVICES=""), timeout=120)
+    assert r.returncode != 0 and "worker" in r.stderr and "failed" in r.stderr, r.stderr[-1000:]
+    assert time.time() - t0 < 60
+    assert not os.path.exists(tmp_path / "f.fa") and not [f for f in os.listdir(tmp_path) if ".part." in f]
+
+
+def test_postprocess_keep_zero_and_short_blocks():
+    """`postprocess -n N` on blocks shorter than N, N = 1 ties and the N = 0 quirk."""
+    import io
+    from oracle import filters
+    from phylign_b200.cli import _postprocess_stream
+    txt = "*q1\t5\nzz9_A\t6\nab1_B\t6\nqq2_C\t5\nqq3_D\t5\nqq4_E\t4\n*q2\t0\n*q3\t1\nxx_F\t8\n"
+    for keep in (0, 1, 2, 3, 4, 5, 9):
+        out = io.StringIO()
+        _postprocess_stream(io.StringIO(txt), out, keep)
+        if keep >= 1:
+            assert out.getvalue() == filters.postprocess_text(txt, keep), keep
+    out = io.StringIO()
+    _postprocess_stream(io.StringIO(txt), out, 1)
+    assert out.getvalue() == "*q1\t5\n_A\t6\n_B\t6\n*q2\t0\n*q3\t1\n_F\t8\n"       # SURVEY Appendix C
