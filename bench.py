@@ -735,6 +735,10 @@ def run_match_db(workdir, tag, fasta, n_gpus, bases, hbm_budget_gb=0):
     return rec, (got, got_fa)
 
 
+class _SkipFiles(Exception):
+    pass
+
+
 def run_ours(args, w, rank, world, local_rank):
     from phylign_b200 import _lib
     from phylign_b200.matcher import Matcher, PinnedBuffer, nccl_unique_id
@@ -859,18 +863,38 @@ def run_ours(args, w, rank, world, local_rank):
 
     # ---- files in -> files out through the product CLI
     e2e_files = None
+    workdir = None
+    if want_files:      # room for the index files?  (a bench line without e2e_files beats no line at all)
+        if rank == 0:
+            workdir = shm_dir("phylign_bench_")
+            need = sum(b["signature_size"] * ((b["n_docs"] + 7) // 8) for b in w["batches"]) + 2 * len(raw) + (4 << 30)
+            free = shutil.disk_usage(workdir).free
+            if free < need:
+                e2e_files = {"value": None, "error": f"{workdir}: {free / 1e9:.0f} GB free, {need / 1e9:.0f} GB needed for "
+                                                     f"the index files: files-in -> files-out run skipped"}
+                shutil.rmtree(workdir, ignore_errors=True)
+                workdir = None
+        workdir = dist.bcast(workdir)
+        want_files = workdir is not None
     if want_files:
-        workdir = dist.bcast(shm_dir("phylign_bench_") if rank == 0 else None)
         try:
             os.makedirs(os.path.join(workdir, "cobs"), exist_ok=True)
             t_w = time.perf_counter()
-            write_index_files(m, ids, os.path.join(workdir, "cobs"))
+            failed = 0
+            try:
+                write_index_files(m, ids, os.path.join(workdir, "cobs"))
+                if rank == 0:
+                    with open(os.path.join(workdir, "batches.txt"), "w") as f:
+                        f.write("\n".join(all_names) + "\n")
+                    write_fasta(os.path.join(workdir, "reads.fa"), raw, w["n_reads"], L)
+                    write_fasta(os.path.join(workdir, "reads150.fa"), raw150, w150["n_reads"], SHORT_READ_LEN)
+            except OSError as e:
+                failed = 1
+                e2e_files = {"value": None, "error": f"writing the bench inputs failed: {e}"}
             t_w = time.perf_counter() - t_w
-            if rank == 0:
-                with open(os.path.join(workdir, "batches.txt"), "w") as f:
-                    f.write("\n".join(all_names) + "\n")
-                write_fasta(os.path.join(workdir, "reads.fa"), raw, w["n_reads"], L)
-                write_fasta(os.path.join(workdir, "reads150.fa"), raw150, w150["n_reads"], SHORT_READ_LEN)
+            if dist.max(failed):
+                e2e_files = e2e_files or {"value": None, "error": "writing the bench inputs failed on another rank"}
+                raise _SkipFiles()
             if world > 1:
                 m.nccl_finalize()           # collective, orderly end of the communicator
             m.close()                       # the CLI needs the HBM
@@ -911,6 +935,8 @@ def run_ours(args, w, rank, world, local_rank):
                             raise SystemExit("capped-budget match-db run produced different files")
                     secondary["streaming_capped_hbm"] = fcap
             dist.barrier()
+        except _SkipFiles:
+            pass
         finally:
             dist.barrier()
             if rank == 0:
