@@ -124,7 +124,7 @@ def main():
             plain = rnd.random() < 0.5
             recs = []
             for j in range(rnd.randrange(1, 40)):
-                ln = rnd.choice([20, 31, 40, 150, 300, 1100, rnd.randrange(1, glen)])
+                ln = min(glen, rnd.choice([20, 31, 40, 150, 300, 1100, rnd.randrange(1, glen)]))
                 a = rnd.randrange(0, glen - ln + 1)
                 s = root[a:a + ln] if rnd.random() < 0.8 else "".join(rnd.choice("ACGT") for _ in range(ln))
                 name = f"q{j}" if plain or rnd.random() < 0.9 else f"q{rnd.randrange(max(1, j))}"   # duplicate names

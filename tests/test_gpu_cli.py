@@ -230,3 +230,11 @@ def test_query_prep_on_device_equals_snakefile_rule(tmp_path):
     r = _run([sys.executable, "-m", "phylign_b200.cli", "match-db", "--cobs-dir", H.GOLDEN, "--batches", str(batches),
               "-q", str(dirty), "--qfile", "queries", "--match-dir", str(tmp_path / "m2"), "-t", "0.7", "-n", "3"])
     assert r.returncode != 0 and "ACGT" in r.stderr
+
+
+def test_pipeline_fuzz_a_few_cases():
+    """tests/fuzz_pipeline.py (random databases + query files through match-db with random blocking /
+    rounds / resume, against cobs_oracle | postprocess_cobs.py | gzip -> filter_queries.py): 6 cases here,
+    40 on 2 GPUs in profiles/r02_fuzz_pipeline_vs_reference_scripts.txt."""
+    r = _run([sys.executable, os.path.join(ROOT, "tests", "fuzz_pipeline.py"), "6", "7"], timeout=900)
+    assert r.returncode == 0 and "6 random databases" in r.stdout, (r.stdout + r.stderr)[-3000:]
