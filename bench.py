@@ -681,7 +681,7 @@ def expected_file_digests(m, records, res, mowner, names_in_rank_order, refs_by_
     return out, fa
 
 
-def run_match_db(workdir, tag, fasta, n_gpus, bases, hbm_budget_gb=0):
+def run_match_db(workdir, tag, fasta, n_gpus, bases, hbm_budget_gb=0, extra=()):
     """One files-in -> files-out run of the product CLI; returns the e2e_files record."""
     import gzip
     outdir = os.path.join(workdir, f"out_{tag}")
@@ -696,6 +696,7 @@ def run_match_db(workdir, tag, fasta, n_gpus, bases, hbm_budget_gb=0):
         cmd += ["--gpus", str(n_gpus)]
     if hbm_budget_gb:
         cmd += ["--hbm-budget", str(int(hbm_budget_gb * 1e9))]
+    cmd += list(extra)
     env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "LOCAL_WORLD_SIZE",
                                                             "MASTER_ADDR", "MASTER_PORT", "GROUP_RANK", "ROLE_RANK")}
     env["PYTHONPATH"] = ROOT + os.pathsep + env.get("PYTHONPATH", "")
@@ -724,6 +725,7 @@ def run_match_db(workdir, tag, fasta, n_gpus, bases, hbm_budget_gb=0):
            "host_s_outside_gpu_and_load": round(host_s, 3), "gpu_match_s": round(ph.get("gpu_match_s", 0.0), 3),
            "writer": timing["writer"], "direct_device_merge": timing.get("direct_device_merge"),
            "rounds": timing.get("rounds"), "overlap_rounds": timing.get("overlap_rounds"),
+           "query_blocks": timing.get("query_blocks"), "filter_written_per_block": timing.get("filter_written_per_block"),
            "gpu_phase_ms_hash_gather_merge": timing.get("gpu_phase_ms_hash_gather_merge"),
            "inputs": {"index_files": len(files), "index_bytes": sum(os.path.getsize(os.path.join(workdir, "cobs", f))
                                                                      for f in os.listdir(os.path.join(workdir, "cobs"))),
@@ -816,6 +818,9 @@ def run_ours(args, w, rank, world, local_rank):
     secondary = {}
     w150 = with_read_len(w, SHORT_READ_LEN)
     raw150 = m.synth_reads(specs, READS_SEED, 0, w150["n_reads"], SHORT_READ_LEN, RANDOM_Q8, ERR_Q16)
+    raw4 = None
+    if want_files and world == 1:      # 4 x the reads for the multi-block file run
+        raw4 = m.synth_reads(specs, READS_SEED, 0, 4 * w["n_reads"], L, RANDOM_Q8, ERR_Q16)
     offs150 = np.arange(w150["n_reads"] + 1, dtype=np.uint64) * SHORT_READ_LEN
     m.set_queries_raw(raw150, offs150)
     s150 = timed_steps(dist, m, max(3, min(args.steps, 10)), 3, rank, local_rank)
@@ -867,7 +872,7 @@ def run_ours(args, w, rank, world, local_rank):
     if want_files:      # room for the index files?  (a bench line without e2e_files beats no line at all)
         if rank == 0:
             workdir = shm_dir("phylign_bench_")
-            need = sum(b["signature_size"] * ((b["n_docs"] + 7) // 8) for b in w["batches"]) + 2 * len(raw) + (4 << 30)
+            need = sum(b["signature_size"] * ((b["n_docs"] + 7) // 8) for b in w["batches"]) + 8 * len(raw) + (4 << 30)
             free = shutil.disk_usage(workdir).free
             if free < need:
                 e2e_files = {"value": None, "error": f"{workdir}: {free / 1e9:.0f} GB free, {need / 1e9:.0f} GB needed for "
@@ -921,6 +926,20 @@ def run_ours(args, w, rank, world, local_rank):
                                          f"{len(bad)} match files, 04_filter equal: {got[1] == exp_fa}")
                     f150, _ = run_match_db(workdir, "150", os.path.join(workdir, "reads150.fa"), world, w150["bases"])
                     secondary["reads150"]["e2e_files"] = f150
+                    if world == 1 and raw4 is not None:
+                        # steady state: 4 query blocks of 100k reads in one run -- the match files of block i are
+                        # formatted, gzipped and appended, and its slice of 04_filter written, while the GPU matches
+                        # block i+1
+                        write_fasta(os.path.join(workdir, "reads4.fa"), raw4, 4 * w["n_reads"], L)
+                        f4, _ = run_match_db(workdir, "4blocks", os.path.join(workdir, "reads4.fa"), world, 4 * w["bases"],
+                                             extra=["--query-block-bases", str(w["bases"])])
+                        if f4.get("value"):
+                            b4 = f4["breakdown_s"]
+                            after = b4["total_in_process"] - b4.get("index_load_wait_s", 0) - b4.get("ctx_create_s", 0) - b4.get("plan_s", 0)
+                            f4["per_block_s_after_load"] = round(after / 4, 3)
+                            f4["per_block_gpu_s"] = round(b4.get("gpu_match_s", 0) / 4, 3)
+                            f4["bases_per_s_after_load"] = 4 * w["bases"] / after
+                        secondary["files_4_query_blocks"] = f4
                     # HBM-overflow streaming: the same run with the per-GPU budget capped so that the
                     # batches need several resident rounds; round r+1 loads while round r is matched
                     per_gpu = sum(b["signature_size"] * 512 for b in w["batches"]) / world

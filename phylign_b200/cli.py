@@ -313,22 +313,32 @@ def _spawn_match_db_workers(a):
                  f"the other workers were stopped")
         if a.filter_out:                       # query-sharded merge: every worker left its slices as parts
             import glob
-            parts = sorted(glob.glob(glob.escape(a.filter_out) + ".part.*"))
-            parts = [p for p in parts if ".tmp." not in p]
+            parts = [p for p in glob.glob(glob.escape(a.filter_out) + ".part.*") if ".tmp." not in p]
             if parts:
-                tmp = f"{a.filter_out}.tmp.{os.getpid()}"
-                with open(tmp, "wb") as out:
-                    for p in parts:             # names sort by (block, rank) = query order
-                        with open(p, "rb") as f:
-                            shutil.copyfileobj(f, out, 16 << 20)
-                os.replace(tmp, a.filter_out)
-                for p in parts:
-                    os.unlink(p)
+                _join_parts(a.filter_out, parts)
     finally:
         for p in procs:
             if p.poll() is None:
                 p.kill()
         shutil.rmtree(tmpdir, ignore_errors=True)
+
+
+def _join_parts(final_path, parts):
+    """04_filter from its parts (named by (block, rank) = query order): rename a single part, else
+    concatenate into tmp + rename; the parts are removed."""
+    import shutil
+    parts = sorted(p for p in parts if ".tmp." not in p)
+    if len(parts) == 1:
+        os.replace(parts[0], final_path)
+        return
+    tmp = f"{final_path}.tmp.{os.getpid()}"
+    with open(tmp, "wb") as out:
+        for p in parts:
+            with open(p, "rb") as f:
+                shutil.copyfileobj(f, out, 16 << 20)
+    os.replace(tmp, final_path)
+    for p in parts:
+        os.unlink(p)
 
 
 def _wait_for_file(path, timeout_s: float):
@@ -532,6 +542,12 @@ def cmd_match_db(a):
             collect = want_filter and rank == 0
         n_merge_queries = qf.n if identity else (len(queries) if queries is not None else 0)
         blocks = qf.block_ranges(a.query_block_bases)
+        # one resident round + plain FASTA: the device merge of a query block is already the final answer
+        # for its queries, so every block's slice of 04_filter is written as a part right away (by the
+        # writer thread) and the parts are joined at the end -- no second merge over all blocks
+        stream_filter = bool(collect and identity and len(plan.rounds) <= 1 and not merged_inputs and
+                             not a.bucket_dir and (not nccl or sharded_merge))
+        part_paths = []
         if a.sanitize_queries:      # raw queries: rule fix_query's base transform on the device, once; the
             with tm.span("sanitize_queries_s"):   # 04_filter FASTA then carries the sanitised sequences too
                 m.fix_bases(qf.seqs[:qf.total_bases])
@@ -561,6 +577,10 @@ def cmd_match_db(a):
             m.nccl_init(_wait_for_file(id_file, float(os.environ.get("PHYLIGN_NCCL_ID_TIMEOUT", 300))), rank, world)
             m.set_option("shard_query_upload", 1)             # every worker passes the same queries
             m.set_option("merge_mode", int(sharded_merge))
+        if stream_filter:                                     # accessions of every batch, from the index headers
+            for b in todo:
+                refs_by_rank[brank[b]] = [_ref_of(n) for n in headers_of[b].doc_names]
+            os.makedirs(os.path.dirname(os.path.abspath(a.filter_out)), exist_ok=True)
         # page-locked result buffers pay off when they are reused block after block; a single
         # (round, block) run fetches once, so plain host memory is cheaper than pinning it
         m.set_option("pinned_results", int(len(blocks) * max(1, len(plan.rounds)) > 2))
@@ -614,7 +634,16 @@ def cmd_match_db(a):
                         if collect:                             # this block's top-N + ties per query and round
                             with tm.span("fetch_merged_s"):
                                 moffs, mc = m.merged()
-                            if identity and len(rounds) == 1 and len(blocks) == 1 and not pieces:
+                            if stream_filter:
+                                lo, hi = own_range(q0, q1)
+                                part = f"{a.filter_out}.part.{bi:06d}.{max(rank, 0):04d}"
+                                part_paths.append(part)
+                                from .cobs_text import write_filter_fasta_native
+                                prev = fut
+                                fut = bg.submit(lambda pv=prev, pa=part, ow=m._merged_owner, l=lo - q0, h=hi - q0, qb=q0:
+                                                (pv.result() if pv is not None else None,
+                                                 write_filter_fasta_native(pa, ow.ptr, qf, refs_by_rank, l, h, qb)))
+                            elif identity and len(rounds) == 1 and len(blocks) == 1 and not pieces:
                                 direct_merged = m._merged_owner   # already the global answer: no host re-merge
                                 direct_arrays = (moffs, mc)
                             else:
@@ -638,6 +667,10 @@ def cmd_match_db(a):
                         except Exception:
                             pass
                     fs.abort()
+                    for pp in part_paths:                       # nothing partial may stay behind
+                        for cand in (pp, f"{pp}.tmp.{os.getpid()}"):
+                            if os.path.exists(cand):
+                                os.unlink(cand)
                     raise
                 wstats.append(fs.stats_dict())
                 round_wall = time.perf_counter() - round_t0
@@ -677,7 +710,11 @@ def cmd_match_db(a):
             for b in todo:
                 if brank[b] not in refs_by_rank:
                     refs_by_rank[brank[b]] = [_ref_of(n) for n in headers_of[b].doc_names]
-        if collect:
+        if stream_filter:
+            if not nccl:                                      # (multi-GPU: the parent joins the workers' parts)
+                with tm.span("write_filter_s"):
+                    _join_parts(a.filter_out, part_paths)
+        elif collect:
             os.makedirs(os.path.dirname(os.path.abspath(a.filter_out)), exist_ok=True)
             with tm.span("final_merge_s"):
                 if direct_merged is None:
@@ -716,7 +753,8 @@ def cmd_match_db(a):
                    "gathered_bytes": int(gathered_total), "rounds": len(rounds), "query_blocks": len(blocks),
                    "overlap_rounds": bool(overlap), "n_queries": qf.n, "bases": int(total_bases),
                    "n_batches": len(todo), "rank": max(rank, 0), "world": world,
-                   "direct_device_merge": bool(identity and len(rounds) == 1 and len(blocks) == 1),
+                   "direct_device_merge": bool(stream_filter or (identity and len(rounds) == 1 and len(blocks) == 1)),
+                   "filter_written_per_block": bool(stream_filter),
                    "native_filter_writer": bool(identity)}
             tmp = a.timing_json + f".tmp.{os.getpid()}"
             with open(tmp, "w") as f:
