@@ -226,12 +226,13 @@ void phy_fasta_free(phy_fasta* f);
 /* filter_queries.py:152-156,195-199 output written straight to `final_path` (tmp + rename):
  * ">{qname} {ref,ref,...}\n{seq}\n" for queries [q_begin, min(q_end, n_queries)) of `m` (a rank that holds
  * one slice of the merged lists writes one part); qname = headers[hoffs[q] .. +name_len[q]).
- * ref_names/ref_offs/ref_counts as in phy_format_filter_fasta. */
+ * ref_names/ref_offs/ref_counts as in phy_format_filter_fasta.  append != 0: `final_path` is a file the
+ * caller owns (its own temporary); the text is appended, nothing is renamed (query blocks written in order). */
 int phy_write_filter_fasta(const char* final_path, const phy_merged* m, const char* headers,
                            const uint64_t* hoffs, const uint32_t* name_len, const char* seqs,
                            const uint64_t* soffs, uint32_t n_batches, const char* const* ref_names,
                            const uint64_t* const* ref_offs, const uint32_t* ref_counts,
-                           uint32_t q_begin, uint32_t q_end, uint64_t* file_bytes /* may be NULL */);
+                           uint32_t q_begin, uint32_t q_end, int append, uint64_t* file_bytes /* may be NULL */);
 
 /* -------------------------------------------------------------- match-file writer
  * The tail of the reference's per-batch pipeline, `... | postprocess_cobs.py -n N | gzip --fast >

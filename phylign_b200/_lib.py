@@ -134,7 +134,7 @@ PROTOTYPES = {
     "phy_fasta_free": (None, [C.POINTER(Fasta)]),
     "phy_write_filter_fasta": (C.c_int, [C.c_char_p, C.POINTER(Merged), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
-                                        C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]),
+                                        C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_uint64)]),
     "phy_mfile_open": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]),
     "phy_mfile_commit": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "phy_mfile_abort": (None, [C.c_void_p]),

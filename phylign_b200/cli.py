@@ -636,13 +636,20 @@ def cmd_match_db(a):
                                 moffs, mc = m.merged()
                             if stream_filter:
                                 lo, hi = own_range(q0, q1)
-                                part = f"{a.filter_out}.part.{bi:06d}.{max(rank, 0):04d}"
-                                part_paths.append(part)
+                                # one GPU: the blocks are appended in order to one temporary file; several GPUs:
+                                # one part per (block, rank), joined by the parent
+                                part = (f"{a.filter_out}.tmp.{os.getpid()}" if not nccl else
+                                        f"{a.filter_out}.part.{bi:06d}.{rank:04d}")
+                                if part not in part_paths:
+                                    part_paths.append(part)
+                                    if not nccl and os.path.exists(part):
+                                        os.unlink(part)
                                 from .cobs_text import write_filter_fasta_native
                                 prev = fut
                                 fut = bg.submit(lambda pv=prev, pa=part, ow=m._merged_owner, l=lo - q0, h=hi - q0, qb=q0:
                                                 (pv.result() if pv is not None else None,
-                                                 write_filter_fasta_native(pa, ow.ptr, qf, refs_by_rank, l, h, qb)))
+                                                 write_filter_fasta_native(pa, ow.ptr, qf, refs_by_rank, l, h, qb,
+                                                                           append=not nccl)))
                             elif identity and len(rounds) == 1 and len(blocks) == 1 and not pieces:
                                 direct_merged = m._merged_owner   # already the global answer: no host re-merge
                                 direct_arrays = (moffs, mc)
@@ -713,7 +720,10 @@ def cmd_match_db(a):
         if stream_filter:
             if not nccl:                                      # (multi-GPU: the parent joins the workers' parts)
                 with tm.span("write_filter_s"):
-                    _join_parts(a.filter_out, part_paths)
+                    if part_paths:
+                        os.replace(part_paths[0], a.filter_out)
+                    else:
+                        _atomic_write(a.filter_out, b"", gz=False)
         elif collect:
             os.makedirs(os.path.dirname(os.path.abspath(a.filter_out)), exist_ok=True)
             with tm.span("final_merge_s"):

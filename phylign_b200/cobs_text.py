@@ -105,12 +105,13 @@ def _ref_tables(ref_names_by_rank):
 
 
 def write_filter_fasta_native(path, merged_ptr, qf, ref_names_by_rank, q_begin: int = 0, q_end: int = 0xFFFFFFFF,
-                              q_base: int = 0) -> int:
+                              q_base: int = 0, append: bool = False) -> int:
     """intermediate/04_filter/{qfile}.fa written by the library (phy_write_filter_fasta) from the flat
     arrays of a fasta.QueryFile: no Python strings, tmp + rename.  [q_begin, q_end): the queries of the
     merged lists to write (a part of the file when they are sharded over GPUs); q_base: query number of
     the merged lists' first query in the file (a query block that starts at record q_base).
-    Returns the file size."""
+    append=True: `path` is the caller's own temporary file, the text is appended and nothing is renamed.
+    Returns the bytes written."""
     import ctypes as C
     import os
     from . import _lib
@@ -120,7 +121,8 @@ def write_filter_fasta_native(path, merged_ptr, qf, ref_names_by_rank, q_begin: 
     _lib.check(L.phy_write_filter_fasta(os.fsencode(path), merged_ptr, qf.headers.ctypes.data,
                                         qf.hoffs.ctypes.data + 8 * q_base, qf.name_len.ctypes.data + 4 * q_base,
                                         qf.seqs.ctypes.data, qf.soffs.ctypes.data + 8 * q_base, nb,
-                                        name_ptrs, off_ptrs, counts.ctypes.data, int(q_begin), int(q_end), C.byref(n)))
+                                        name_ptrs, off_ptrs, counts.ctypes.data, int(q_begin), int(q_end), int(append),
+                                        C.byref(n)))
     return n.value
 
 

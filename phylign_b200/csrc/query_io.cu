@@ -148,11 +148,13 @@ extern "C" int phy_write_filter_fasta(const char* final_path, const phy_merged* 
                                       const uint64_t* hoffs, const uint32_t* name_len, const char* seqs,
                                       const uint64_t* soffs, uint32_t n_batches, const char* const* ref_names,
                                       const uint64_t* const* ref_offs, const uint32_t* ref_counts,
-                                      uint32_t q_begin, uint32_t q_end, uint64_t* file_bytes) {
+                                      uint32_t q_begin, uint32_t q_end, int append, uint64_t* file_bytes) {
     if (!final_path || !m || !headers || !hoffs || !name_len || !seqs || !soffs) return PHY_ERR_ARG;
     q_end = std::min(q_end, m->n_queries);
-    std::string tmp = std::string(final_path) + ".tmp." + std::to_string((long)getpid());
-    int fd = ::open(tmp.c_str(), O_WRONLY | O_CREAT | O_TRUNC | O_CLOEXEC, 0644);
+    // append != 0: the caller owns the (temporary) file and its final rename; blocks are appended in order
+    std::string tmp = append ? std::string(final_path)
+                             : std::string(final_path) + ".tmp." + std::to_string((long)getpid());
+    int fd = ::open(tmp.c_str(), O_WRONLY | O_CREAT | O_CLOEXEC | (append ? O_APPEND : O_TRUNC), 0644);
     if (fd < 0) {
         phy_set_error(nullptr, "cannot create %s: %s", tmp.c_str(), strerror(errno));
         return PHY_ERR_IO;
@@ -191,7 +193,7 @@ extern "C" int phy_write_filter_fasta(const char* final_path, const phy_merged* 
     }
     if (ok) flush();
     ok = (::close(fd) == 0) && ok;
-    if (ok && ::rename(tmp.c_str(), final_path) != 0) ok = false;
+    if (ok && !append && ::rename(tmp.c_str(), final_path) != 0) ok = false;
     if (!ok) {
         if (rc == PHY_OK) {
             phy_set_error(nullptr, "cannot write %s: %s", final_path, strerror(errno));
@@ -199,7 +201,7 @@ extern "C" int phy_write_filter_fasta(const char* final_path, const phy_merged* 
         } else {
             phy_set_error(nullptr, "merged candidate refers to an unknown batch/document");
         }
-        ::unlink(tmp.c_str());
+        if (!append) ::unlink(tmp.c_str());
         return rc;
     }
     if (file_bytes) *file_bytes = total;
