@@ -583,7 +583,7 @@ def cmd_match_db(a):
             os.makedirs(os.path.dirname(os.path.abspath(a.filter_out)), exist_ok=True)
         # page-locked result buffers pay off when they are reused block after block; a single
         # (round, block) run fetches once, so plain host memory is cheaper than pinning it
-        m.set_option("pinned_results", int(len(blocks) * max(1, len(plan.rounds)) > 2))
+        m.set_option("pinned_results", int(len(blocks) * max(1, len(plan.rounds)) > 8))   # (2 pool generations to pin)
         wstats, gpu_phase_ms, gathered_total, n_writer_blocks = [], np.zeros(3), 0, 0
         direct_merged = direct_arrays = None                   # set when one device merge is already the final answer
         bg = _TPE(max_workers=1)                               # the writer thread (format + gzip + append)
