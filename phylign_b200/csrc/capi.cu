@@ -396,6 +396,7 @@ extern "C" int phy_index_begin(phy_ctx* ctx, const char* batch_name, uint32_t te
     ix.d.batch_rank = (uint32_t)slot % PHY_MAX_BATCH_RANK;
     ctx->idx[slot] = ix;
     ctx->indexes_dirty = true;
+    ctx->index_version++;
     *idx_id = (int)slot;
     return PHY_OK;
 }
@@ -449,6 +450,7 @@ extern "C" int phy_index_commit(phy_ctx* ctx, int idx_id) {
     if (ctx->up_stream) PHY_CUDA(ctx, cudaStreamSynchronize(ctx->up_stream));
     ix->committed = true;
     ctx->indexes_dirty = true;
+    ctx->index_version++;
     return PHY_OK;
 }
 
@@ -460,6 +462,7 @@ extern "C" int phy_index_evict(phy_ctx* ctx, int idx_id) {
     phy_dev_free(ctx, ix->ref_rank_mut, (size_t)ix->d.n_docs * sizeof(uint32_t), true);
     *ix = HostIndex();
     ctx->indexes_dirty = true;
+    ctx->index_version++;
     ctx->have_match = ctx->have_merged = false;
     return PHY_OK;
 }
@@ -482,12 +485,14 @@ extern "C" int phy_index_set_ranks(phy_ctx* ctx, int idx_id, uint32_t batch_rank
     }
     ix->d.batch_rank = batch_rank;
     ctx->indexes_dirty = true;
+    ctx->index_version++;
     return PHY_OK;
 }
 
 extern "C" int phy_index_set_active(phy_ctx* ctx, int idx_id, int active) {
     HostIndex* ix = get_index(ctx, idx_id);
     if (!ix) return PHY_ERR_ARG;
+    ctx->index_version++;
     ix->active = active != 0;  // takes effect with the next phy_match_run; fetched / fetchable results stay valid
     return PHY_OK;
 }
@@ -558,6 +563,7 @@ extern "C" int phy_queries_set(phy_ctx* ctx, const char* seq_concat, const uint6
     ctx->h_qoffs.assign(offs, offs + nq + 1);
     ctx->total_bases = offs[nq] - offs[0];
     ctx->have_queries = true;
+    ctx->kmer_tables_valid = ctx->ioffs_valid = ctx->gather_tables_valid = false;
     ctx->hashes_valid = false;
     ctx->have_match = ctx->have_merged = false;
     ctx->q_term_size = 0;  // k-mer tables are (re)built by phy_match_run for the resident indexes' k
@@ -600,30 +606,37 @@ extern "C" int phy_fix_bases(phy_ctx* ctx, char* bases, uint64_t n) {
 static int prepare_hashes(phy_ctx* ctx, uint32_t k, uint32_t canon, uint32_t nh) {
     if (ctx->hashes_valid && ctx->q_term_size == k && ctx->q_canon == canon && ctx->q_num_hashes >= nh) return PHY_OK;
     const uint32_t nq = ctx->nq;
-    ctx->h_koffs.resize(nq + 1);
-    ctx->h_nk.resize(nq + 1);
-    uint64_t run = 0;
-    for (uint32_t q = 0; q < nq; q++) {
-        uint64_t L = ctx->h_qoffs[q + 1] - ctx->h_qoffs[q];
-        uint64_t K = L >= k ? L - k + 1 : 0;
-        if (K > 0xFFFFFFF0ull) {
-            phy_set_error(ctx, "query #%u too long", q);
-            return PHY_ERR_ARG;
+    // the k-mer offset tables depend on the query set and k only: built and uploaded once per
+    // phy_queries_set, not once per pass (the hashes themselves are recomputed by every pass)
+    if (!ctx->kmer_tables_valid || ctx->q_term_size != k) {
+        ctx->h_koffs.resize(nq + 1);
+        ctx->h_nk.resize(nq + 1);
+        uint64_t run = 0;
+        for (uint32_t q = 0; q < nq; q++) {
+            uint64_t L = ctx->h_qoffs[q + 1] - ctx->h_qoffs[q];
+            uint64_t K = L >= k ? L - k + 1 : 0;
+            if (K > 0xFFFFFFF0ull) {
+                phy_set_error(ctx, "query #%u too long", q);
+                return PHY_ERR_ARG;
+            }
+            ctx->h_koffs[q] = run;
+            ctx->h_nk[q] = (uint32_t)K;
+            run += K;
         }
-        ctx->h_koffs[q] = run;
-        ctx->h_nk[q] = (uint32_t)K;
-        run += K;
+        ctx->h_koffs[nq] = run;
+        ctx->h_nk[nq] = 0;
+        ctx->total_kmers = run;
+        ctx->q_term_size = k;
+        PHY_TRY(phy_ensure(ctx, ctx->d_koffs, nq + 2));
+        PHY_TRY(phy_ensure(ctx, ctx->d_nk, nq + 2));
+        PHY_TRY(phy_h2d(ctx, ctx->d_koffs.p, ctx->h_koffs.data(), (nq + 1) * sizeof(uint64_t)));
+        PHY_TRY(phy_h2d(ctx, ctx->d_nk.p, ctx->h_nk.data(), (nq + 1) * sizeof(uint32_t)));
+        ctx->kmer_tables_valid = true;
+        ctx->ioffs_valid = false;
+        ctx->gather_tables_valid = false;
     }
-    ctx->h_koffs[nq] = run;
-    ctx->h_nk[nq] = 0;
-    ctx->total_kmers = run;
-    ctx->q_term_size = k;
     ctx->q_canon = canon;
     ctx->q_num_hashes = nh;
-    PHY_TRY(phy_ensure(ctx, ctx->d_koffs, nq + 2));
-    PHY_TRY(phy_ensure(ctx, ctx->d_nk, nq + 2));
-    PHY_TRY(phy_h2d(ctx, ctx->d_koffs.p, ctx->h_koffs.data(), (nq + 1) * sizeof(uint64_t)));
-    PHY_TRY(phy_h2d(ctx, ctx->d_nk.p, ctx->h_nk.data(), (nq + 1) * sizeof(uint32_t)));
     return phy_launch_hash(ctx);
 }
 
@@ -673,6 +686,7 @@ extern "C" int phy_match_run(phy_ctx* ctx, const phy_match_params* p, uint32_t m
     PHY_CUDA(ctx, cudaEventRecord(ctx->ev_ph[0], ctx->stream));
     if (empty_rank) {
         ctx->h_nk.assign((size_t)ctx->nq + 1, 0);
+        ctx->kmer_tables_valid = false;
         ctx->n_units = ctx->n_hits = 0;
         ctx->units_ordered = true;
         PHY_TRY(phy_ensure(ctx, ctx->d_qcount, ctx->nq + 1));
@@ -824,6 +838,7 @@ extern "C" int phy_merge_host(phy_ctx* ctx, uint32_t n_queries, uint32_t top_n, 
         }
     PHY_CUDA(ctx, cudaSetDevice(ctx->device));
     ctx->have_queries = ctx->have_match = false;  // the query set of this ctx is replaced
+    ctx->kmer_tables_valid = ctx->ioffs_valid = ctx->gather_tables_valid = false;
     ctx->have_merged = false;
     PHY_TRY(phy_merge_host_impl(ctx, n_queries, top_n, offs, cands));
     PHY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -930,6 +945,7 @@ extern "C" int phy_index_synth(phy_ctx* ctx, int idx_id, const phy_synth_spec* s
     ix->pushed = ix->body_bytes;
     ix->committed = true;
     ctx->indexes_dirty = true;
+    ctx->index_version++;
     return PHY_OK;
 }
 

@@ -881,77 +881,92 @@ int phy_launch_gather(phy_ctx* ctx, const phy_match_params* p) {
     // per-query minimum score T (host double arithmetic, identical to the oracle / cobs) and the
     // query classes by k-mer count: <= 255 (8 counter planes), <= 1023 (10), <= 16383 (14) are fused
     // in the ring kernel; longer ones go through the chunked dense-score path.
-    std::vector<uint32_t> T(ctx->nq), shortq, fastq, midq, slowq;
-    for (uint32_t q = 0; q < ctx->nq; q++) {
-        double x = p->threshold * (double)ctx->h_nk[q];
-        double r = p->floor_mode ? floor(x) : ceil(x);
-        T[q] = r < 0 ? 0u : (r > 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)r);
-        const uint32_t K = ctx->h_nk[q];
-        if (K == 0) continue;
-        if (K <= PHY_SHORT_KMAX) shortq.push_back(q);
-        else if (K <= PHY_FUSED_KMAX) fastq.push_back(q);
-        else if (K <= PHY_LONG_KMAX) midq.push_back(q);
-        else slowq.push_back(q);
+    // These tables depend on the query set, the threshold and the set of active indexes only: they are
+    // built and uploaded when one of those changes, not once per pass.
+    GatherTables& gt = ctx->gt;
+    if (!ctx->gather_tables_valid || gt.threshold != p->threshold || gt.floor_mode != p->floor_mode ||
+        gt.index_version != ctx->index_version) {
+        std::vector<uint32_t> T(ctx->nq), shortq, fastq, midq;
+        gt.slowq.clear();
+        for (uint32_t q = 0; q < ctx->nq; q++) {
+            double x = p->threshold * (double)ctx->h_nk[q];
+            double r = p->floor_mode ? floor(x) : ceil(x);
+            T[q] = r < 0 ? 0u : (r > 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)r);
+            const uint32_t K = ctx->h_nk[q];
+            if (K == 0) continue;
+            if (K <= PHY_SHORT_KMAX) shortq.push_back(q);
+            else if (K <= PHY_FUSED_KMAX) fastq.push_back(q);
+            else if (K <= PHY_LONG_KMAX) midq.push_back(q);
+            else gt.slowq.push_back(q);
+        }
+        // longest first: balances the tail and keeps co-resident groups of a warp similar
+        auto sort_by_len_desc = [&](std::vector<uint32_t>& v) {  // stable counting sort: K <= 16383
+            if (v.size() < 2) return;
+            uint32_t kmin = 0xFFFFFFFFu, kmax = 0;
+            for (uint32_t q : v) { kmin = std::min(kmin, ctx->h_nk[q]); kmax = std::max(kmax, ctx->h_nk[q]); }
+            if (kmin == kmax) return;  // all reads equally long (the common case): nothing to do
+            std::vector<uint32_t> start(kmax - kmin + 2, 0), out(v.size());
+            for (uint32_t q : v) start[kmax - ctx->h_nk[q] + 1]++;
+            for (size_t i = 1; i < start.size(); i++) start[i] += start[i - 1];
+            for (uint32_t q : v) out[start[kmax - ctx->h_nk[q]]++] = q;
+            v.swap(out);
+        };
+        sort_by_len_desc(shortq);
+        sort_by_len_desc(fastq);
+        sort_by_len_desc(midq);
+        // device list layout: [10-plane | 8-plane | 14-plane]; the first two together are "K <= 1023"
+        gt.n_fast8 = (uint32_t)shortq.size();
+        gt.n_fast10 = (uint32_t)fastq.size();
+        gt.n_fast14 = (uint32_t)midq.size();
+        gt.fastq = fastq;
+        gt.fastq.insert(gt.fastq.end(), shortq.begin(), shortq.end());
+        gt.fastq.insert(gt.fastq.end(), midq.begin(), midq.end());   // every fused-capable query
+        PHY_TRY(phy_ensure(ctx, ctx->d_T, ctx->nq + 1));
+        PHY_TRY(phy_h2d(ctx, ctx->d_T.p, T.data(), T.size() * sizeof(uint32_t)));
+        PHY_TRY(phy_ensure(ctx, ctx->d_qlist, ctx->nq + 1));
+        if (!gt.fastq.empty()) PHY_TRY(phy_h2d(ctx, ctx->d_qlist.p, gt.fastq.data(), gt.fastq.size() * sizeof(uint32_t)));
+
+        // index classes: one launch per (lanes-per-row class, number of hash functions, query class);
+        // rows wider than 512 B take the general path for every query
+        gt.classes.clear();
+        for (size_t i = 0; i < ctx->idx.size(); i++) {
+            const HostIndex& ix = ctx->idx[i];
+            if (!ix.alive || !ix.committed || !ix.active) continue;
+            if (ix.d.stride > PHY_CHUNK_BYTES) continue;
+            int c = 0;
+            while ((1 << c) < ix.lpr) c++;
+            GatherTables::IdxClass* k = nullptr;
+            for (auto& x : gt.classes)
+                if (x.c == c && x.h == ix.d.num_hashes) k = &x;
+            if (!k) {
+                gt.classes.push_back(GatherTables::IdxClass{c, ix.d.num_hashes, {}, 0});
+                k = &gt.classes.back();
+            }
+            k->ids.push_back((uint32_t)i);
+        }
+        std::sort(gt.classes.begin(), gt.classes.end(), [](const GatherTables::IdxClass& x, const GatherTables::IdxClass& y) {
+            return x.h != y.h ? x.h < y.h : x.c < y.c;
+        });
+        std::vector<uint32_t> class_flat;
+        for (auto& k : gt.classes) { k.off = class_flat.size(); class_flat.insert(class_flat.end(), k.ids.begin(), k.ids.end()); }
+        if (!class_flat.empty()) {
+            PHY_TRY(phy_ensure(ctx, ctx->d_class, class_flat.size()));
+            PHY_TRY(phy_h2d(ctx, ctx->d_class.p, class_flat.data(), class_flat.size() * sizeof(uint32_t)));
+        }
+        gt.threshold = p->threshold;
+        gt.floor_mode = p->floor_mode;
+        gt.index_version = ctx->index_version;
+        ctx->gather_tables_valid = true;
     }
-    // longest first: balances the tail and keeps co-resident groups of a warp similar
-    auto sort_by_len_desc = [&](std::vector<uint32_t>& v) {  // stable counting sort: K <= 16383
-        if (v.size() < 2) return;
-        uint32_t kmin = 0xFFFFFFFFu, kmax = 0;
-        for (uint32_t q : v) { kmin = std::min(kmin, ctx->h_nk[q]); kmax = std::max(kmax, ctx->h_nk[q]); }
-        if (kmin == kmax) return;  // all reads equally long (the common case): nothing to do
-        std::vector<uint32_t> start(kmax - kmin + 2, 0), out(v.size());
-        for (uint32_t q : v) start[kmax - ctx->h_nk[q] + 1]++;
-        for (size_t i = 1; i < start.size(); i++) start[i] += start[i - 1];
-        for (uint32_t q : v) out[start[kmax - ctx->h_nk[q]]++] = q;
-        v.swap(out);
-    };
-    sort_by_len_desc(shortq);
-    sort_by_len_desc(fastq);
-    sort_by_len_desc(midq);
-    // device list layout: [10-plane | 8-plane | 14-plane]; the first two together are "K <= 1023"
-    const uint32_t n_fast8 = (uint32_t)shortq.size(), n_fast10 = (uint32_t)fastq.size(), n_fast14 = (uint32_t)midq.size();
+    const std::vector<uint32_t>& fastq = gt.fastq;
+    const std::vector<uint32_t>& slowq = gt.slowq;
+    const std::vector<GatherTables::IdxClass>& classes = gt.classes;
+    using IdxClass = GatherTables::IdxClass;
+    const uint32_t n_fast8 = gt.n_fast8, n_fast10 = gt.n_fast10, n_fast14 = gt.n_fast14;
     const uint32_t n_le1023 = n_fast10 + n_fast8;
-    std::vector<uint32_t> le1023 = fastq;
-    le1023.insert(le1023.end(), shortq.begin(), shortq.end());
-    fastq = le1023;
-    fastq.insert(fastq.end(), midq.begin(), midq.end());   // every fused-capable query
-    PHY_TRY(phy_ensure(ctx, ctx->d_T, ctx->nq + 1));
-    PHY_TRY(phy_h2d(ctx, ctx->d_T.p, T.data(), T.size() * sizeof(uint32_t)));
-    PHY_TRY(phy_ensure(ctx, ctx->d_qlist, ctx->nq + 1));
-    if (!fastq.empty()) PHY_TRY(phy_h2d(ctx, ctx->d_qlist.p, fastq.data(), fastq.size() * sizeof(uint32_t)));
+    uint32_t* d_class = ctx->d_class.p;
     PHY_TRY(phy_ensure(ctx, ctx->d_qcount, ctx->nq + 1));
     PHY_TRY(phy_ensure(ctx, ctx->d_counters, 8));
-
-    // index classes: one launch per (lanes-per-row class, number of hash functions, query class);
-    // rows wider than 512 B take the general path for every query
-    struct IdxClass { int c; uint32_t h; std::vector<uint32_t> ids; size_t off; };
-    std::vector<IdxClass> classes;
-    for (size_t i = 0; i < ctx->idx.size(); i++) {
-        const HostIndex& ix = ctx->idx[i];
-        if (!ix.alive || !ix.committed || !ix.active) continue;
-        if (ix.d.stride > PHY_CHUNK_BYTES) continue;
-        int c = 0;
-        while ((1 << c) < ix.lpr) c++;
-        IdxClass* k = nullptr;
-        for (auto& x : classes)
-            if (x.c == c && x.h == ix.d.num_hashes) k = &x;
-        if (!k) {
-            classes.push_back(IdxClass{c, ix.d.num_hashes, {}, 0});
-            k = &classes.back();
-        }
-        k->ids.push_back((uint32_t)i);
-    }
-    std::sort(classes.begin(), classes.end(), [](const IdxClass& x, const IdxClass& y) {
-        return x.h != y.h ? x.h < y.h : x.c < y.c;
-    });
-    std::vector<uint32_t> class_flat;
-    for (auto& k : classes) { k.off = class_flat.size(); class_flat.insert(class_flat.end(), k.ids.begin(), k.ids.end()); }
-    uint32_t* d_class = nullptr;
-    if (!class_flat.empty()) {
-        PHY_TRY(phy_ensure(ctx, ctx->d_class, class_flat.size()));
-        d_class = ctx->d_class.p;
-        PHY_TRY(phy_h2d(ctx, d_class, class_flat.data(), class_flat.size() * sizeof(uint32_t)));
-    }
 
     uint64_t units_cap = ctx->d_units.cap, hits_cap = ctx->d_hits.cap;
     // first sizing guess for a new workload (an overflow is still caught: the pass reports the needed

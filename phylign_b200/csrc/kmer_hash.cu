@@ -236,15 +236,20 @@ int phy_launch_hash(phy_ctx* ctx) {
     }
     if (ctx->q_term_size == 31) {
         // work items = runs of KPT consecutive k-mers of one query
-        std::vector<uint64_t> ioffs(ctx->nq + 1);
-        uint64_t run = 0;
-        for (uint32_t q = 0; q < ctx->nq; q++) {
-            ioffs[q] = run;
-            run += (ctx->h_nk[q] + KPT - 1) / KPT;
+        if (!ctx->ioffs_valid) {
+            std::vector<uint64_t> ioffs(ctx->nq + 1);
+            uint64_t run = 0;
+            for (uint32_t q = 0; q < ctx->nq; q++) {
+                ioffs[q] = run;
+                run += (ctx->h_nk[q] + KPT - 1) / KPT;
+            }
+            ioffs[ctx->nq] = run;
+            PHY_TRY(phy_ensure(ctx, ctx->d_ioffs, ctx->nq + 2));
+            PHY_TRY(phy_h2d(ctx, ctx->d_ioffs.p, ioffs.data(), ioffs.size() * sizeof(uint64_t)));
+            ctx->n_hash_items = run;
+            ctx->ioffs_valid = true;
         }
-        ioffs[ctx->nq] = run;
-        PHY_TRY(phy_ensure(ctx, ctx->d_ioffs, ctx->nq + 2));
-        PHY_TRY(phy_h2d(ctx, ctx->d_ioffs.p, ioffs.data(), ioffs.size() * sizeof(uint64_t)));
+        const uint64_t run = ctx->n_hash_items;
         const uint64_t nb = (run + 255) / 256;
         kmer_hash31_roll_kernel<<<(unsigned)nb, 256, 0, ctx->stream>>>(
             ctx->d_seq.p, ctx->d_qoffs.p, ctx->d_koffs.p, ctx->d_ioffs.p, ctx->nq, run, ctx->total_kmers,

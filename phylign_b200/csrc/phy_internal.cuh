@@ -57,6 +57,17 @@ struct HostIndex {
     int lpr = 32;  // lanes per row chunk (1,2,4,8,16,32)
 };
 
+// host copies of the per-(query set, threshold, index set) launch tables of the gather pass
+struct GatherTables {
+    struct IdxClass { int c; uint32_t h; std::vector<uint32_t> ids; size_t off; };
+    std::vector<IdxClass> classes;          // (lanes-per-row class, number of hash functions) -> index ids
+    std::vector<uint32_t> fastq, slowq;     // fused-capable queries [10-plane | 8-plane | 14-plane]; K > 16383
+    uint32_t n_fast8 = 0, n_fast10 = 0, n_fast14 = 0;
+    double threshold = -1.0;
+    uint32_t floor_mode = 0;
+    uint64_t index_version = ~0ull;
+};
+
 struct phy_ctx {
     int device = 0, n_sm = 148;
     bool prune = true;    // PHY_NO_PRUNE=1 switches the exact threshold pruning of the ring kernel off
@@ -99,6 +110,11 @@ struct phy_ctx {
     DevBuf<uint32_t> d_nk, d_T, d_qlist, d_class;
     bool hashes_valid = false;
     bool hash_check_pending = false;  // K1's error word has not been read yet
+    // per-query-set tables already on the device (rebuilt after phy_queries_set / a change of k, threshold, index set)
+    bool kmer_tables_valid = false, ioffs_valid = false, gather_tables_valid = false;
+    GatherTables gt;
+    uint64_t n_hash_items = 0;                          // K1 work items of the current query set
+    uint64_t index_version = 0;                         // bumped whenever the set of (active) indexes changes
 
     // match outputs (device resident until fetched)
     bool have_match = false, have_merged = false;
