@@ -533,3 +533,49 @@ def test_postprocess_keep_zero_and_short_blocks():
     out = io.StringIO()
     _postprocess_stream(io.StringIO(txt), out, 1)
     assert out.getvalue() == "*q1\t5\n_A\t6\n_B\t6\n*q2\t0\n*q3\t1\n_F\t8\n"
+
+
+def test_benchmark_log_has_the_reference_columns(tmp_path):
+    """--benchmark-dir files start with the header scripts/benchmark.py writes (its :33-46), so the
+    reference's log readers find the 8 columns they know before the match-stage columns."""
+    from phylign_b200.cli import _write_benchmark_log
+    p = tmp_path / "logs" / "benchmarks" / "run_cobs" / "b__01____q.txt"
+    _write_benchmark_log(str(p), "phylign_b200 match-db (round 0)", 1.25, [("batch", "b__01"), ("gpu_ms", "3.5")])
+    lines = p.read_text().splitlines()
+    assert lines[0].startswith("# Benchmarking command: ")
+    head, vals = lines[1].split("\t"), lines[2].split("\t")
+    assert head[:8] == ["real(s)", "sys(s)", "user(s)", "percent_CPU", "max_RAM(kb)", "FS_inputs", "FS_outputs",
+                        "elapsed_time_alt(s)"]
+    assert len(head) == len(vals) == 10 and float(vals[0]) == 1.25 and vals[8] == "b__01"
+
+
+def test_join_parts_orders_by_block_then_rank(tmp_path):
+    from phylign_b200.cli import _join_parts
+    out = tmp_path / "q.fa"
+    for name, txt in (("000001.0000", "C"), ("000000.0001", "B"), ("000000.0000", "A"), ("000001.0001", "D")):
+        (tmp_path / f"q.fa.part.{name}").write_text(txt)
+    _join_parts(str(out), [str(p) for p in tmp_path.iterdir()])
+    assert out.read_text() == "ABCD" and os.listdir(tmp_path) == ["q.fa"]
+    (tmp_path / "q.fa.part.000000.0000").write_text("only")
+    _join_parts(str(out), [str(tmp_path / "q.fa.part.000000.0000")])
+    assert out.read_text() == "only" and os.listdir(tmp_path) == ["q.fa"]
+
+
+def test_query_block_ranges_cover_every_record_once():
+    """QueryFile.block_ranges: consecutive, non-empty, within the base budget unless a single record exceeds it."""
+    import random
+    import tempfile
+    from phylign_b200.fasta import QueryFile
+    rnd = random.Random(4)
+    for _ in range(20):
+        lens = [rnd.choice([1, 31, 150, 1000, 5000]) for _ in range(rnd.randrange(1, 60))]
+        with tempfile.NamedTemporaryFile("w", suffix=".fa", delete=False) as f:
+            f.write("".join(f">r{i}\n{'A' * n}\n" for i, n in enumerate(lens)))
+        q = QueryFile(f.name)
+        os.unlink(f.name)
+        budget = rnd.choice([1, 100, 1000, 6000, 10 ** 9])
+        br = q.block_ranges(budget)
+        assert br[0][0] == 0 and br[-1][1] == len(lens)
+        for (a, b), nxt in zip(br, br[1:] + [(len(lens), None)]):
+            assert b > a and b == nxt[0]
+            assert sum(lens[a:b]) <= budget or b == a + 1
