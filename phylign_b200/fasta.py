@@ -14,10 +14,12 @@ import os
 
 
 def _open_text(path):
+    # newline="\n": lines end at LF only, like std::getline in cobs and like phy_fasta_read (a lone CR
+    # inside a line is data, a trailing CR is stripped by the readers)
     p = str(path)
     if p.endswith(".gz"):
-        return gzip.open(p, "rt")
-    return open(p, "r")
+        return gzip.open(p, "rt", newline="\n")
+    return open(p, "r", newline="\n")
 
 
 def read_cobs_records(path):

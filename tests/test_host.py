@@ -579,3 +579,23 @@ def test_query_block_ranges_cover_every_record_once():
         for (a, b), nxt in zip(br, br[1:] + [(len(lens), None)]):
             assert b > a and b == nxt[0]
             assert sum(lens[a:b]) <= budget or b == a + 1
+
+
+def test_native_reader_equals_python_reader_on_random_text(tmp_path):
+    """phy_fasta_read vs read_cobs_records on 300 random line soups ('>' / ';' headers, blank and CRLF lines,
+    text before the first header, missing final newline, '@' / '+' lines)."""
+    import random
+    from phylign_b200.fasta import QueryFile, read_cobs_records
+    rnd = random.Random(12)
+    tokens = [">q", ">q x y", ";c", "ACGT", "acgtn", "", "\r", "@r", "+", "GG\r", ">", "TTTTTTTTTT" * 8, " ", ">q\tz"]
+    for case in range(300):
+        lines = [rnd.choice(tokens) + (str(rnd.randrange(9)) if rnd.random() < 0.3 else "") for _ in range(rnd.randrange(0, 25))]
+        txt = "\n".join(lines) + ("\n" if rnd.random() < 0.8 else "")
+        p = tmp_path / "r.fa"
+        p.write_bytes(txt.encode())
+        want = read_cobs_records(str(p))
+        q = QueryFile(str(p))
+        got = [(h, s.decode()) for h, s in q.records()]
+        assert got == want, (case, txt)
+        assert q.n == len(want) and q.total_bases == sum(len(s) for _, s in want)
+        assert q.names() == [h.split(" ")[0] for h, _ in want]
