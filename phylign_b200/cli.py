@@ -37,7 +37,7 @@ import numpy as np
 
 from . import fasta
 from .cobs_index import ref_of as _ref_of
-from .cobs_text import format_cobs_text_fast, format_filter_fasta_fast
+from .cobs_text import format_filter_fasta_fast
 
 
 def _die(msg, code=1):
@@ -71,19 +71,6 @@ def _postprocess_stream(fin, fout, keep: int):
         else:
             block.append(x)
     flush(block)
-
-
-def query_blocks(records, max_bases: int):
-    """Split the query list into consecutive blocks of at most max_bases bases (at least one
-    record each): the k-mer hashes of a block (8 B per base) must fit in HBM beside the indexes."""
-    start, acc = 0, 0
-    for i, (_, seq) in enumerate(records):
-        if i > start and acc + len(seq) > max_bases:
-            yield start, records[start:i]
-            start, acc = i, 0
-        acc += len(seq)
-    if start < len(records) or not records:
-        yield start, records[start:]
 
 
 # ------------------------------------------------------------------------------------ cobs query

@@ -21,7 +21,7 @@ import sys
 import time
 
 from . import fasta
-from .cobs_text import format_cobs_text_fast
+from .cobs_text import format_cobs_text_arrays
 
 
 class MatchService:
@@ -65,15 +65,15 @@ class MatchService:
         hdr = self.m.indexes[idx].header
         if req.get("index_sizes") is not None and req["index_sizes"] != hdr.header_size + hdr.body_size:
             raise ValueError(f"--index-sizes {req['index_sizes']} != header {hdr.header_size} + body {hdr.body_size}")
-        from .cli import query_blocks
-        records = fasta.read_cobs_records(req["query"])
+        qf = fasta.QueryFile(req["query"])                  # flat arrays (native reader)
         out = []
-        for _, block in query_blocks(records, int(req.get("query_block_bases", 2 * 10 ** 9))):
-            self.m.set_queries(block)
+        for q0, q1 in qf.block_ranges(int(req.get("query_block_bases", 2 * 10 ** 9))):
+            self.m.set_queries_raw(qf.seqs, qf.soffs[q0:q1 + 1])
             # only this index takes part: the others stay resident but are not queried
             res = self.m.match(req["threshold"], top_n=req.get("top_n", 0), floor_mode=req.get("floor", False),
                                only=[idx])
-            out.append(format_cobs_text_fast(block, res, self.m.indexes[idx], strip_prefix=req.get("top_n", 0) > 0))
+            out.append(format_cobs_text_arrays(qf.headers, qf.hoffs[q0:q1 + 1], res, self.m.indexes[idx],
+                                               strip_prefix=req.get("top_n", 0) > 0))
         self.stats["queries"] += 1
         return b"".join(out)
 

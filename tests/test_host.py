@@ -273,17 +273,6 @@ def test_candidate_buckets_equal_batch_align_load_qdicts():
         assert format_bucket_tsv(got.get(r, [])).count("\n") == len(want)
 
 
-def test_query_blocks_partition():
-    from phylign_b200.cli import query_blocks
-    recs = [("a", "A" * 10), ("b", "C" * 10), ("c", "G" * 25), ("d", "T"), ("e", "")]
-    blocks = list(query_blocks(recs, 20))
-    assert [s for s, _ in blocks] == [0, 2, 3]
-    assert [r for _, b in blocks for r in b] == recs                    # order kept, nothing lost
-    assert all(sum(len(s) for _, s in b) <= 20 or len(b) == 1 for _, b in blocks)
-    assert list(query_blocks(recs, 10 ** 9)) == [(0, recs)]
-    assert list(query_blocks([], 5)) == [(0, [])]
-
-
 def test_header_roundtrip_property():
     """ClassicHeader.to_bytes / read_header round trip on random headers (hypothesis), including
     bodies whose first bytes look like a name table, and chunked/pipe-like reads."""
