@@ -112,9 +112,11 @@ __global__ void __launch_bounds__(256) kmer_hash_kernel(
     for (uint32_t j = 0; j < num_hashes; j++) hashes[(uint64_t)j * total_kmers + g] = xxh64_packed(w, k, j);
 }
 
-// k = 31 fast path: one thread rolls over 4 consecutive k-mers of one query (34 byte loads
-// for 4 k-mers instead of 124) and turns the canonical 2-bit value into its 31 ASCII bytes
-// with a 256-entry shared-memory table (4 bases -> 4 letters per lookup).
+// k = 31 fast path: one thread takes 4 consecutive k-mers of one query.  Their 34 bases are read as ten
+// aligned 32-bit words and packed to 2 bits four letters at a time (round 1 rolled byte by byte: ~170 of
+// its ~390 instructions per k-mer were the per-base pack / validate / reverse-complement updates); the four
+// k-mers are 62-bit windows of the packed stream, the reverse complement is a bit reversal; the canonical
+// value becomes its 31 ASCII bytes through a 256-entry shared-memory table (4 bases -> 4 letters).
 constexpr int KPT = 4;  // k-mers per thread
 __global__ void __launch_bounds__(256) kmer_hash31_roll_kernel(
     const char* __restrict__ seq, const uint64_t* __restrict__ qoffs, const uint64_t* __restrict__ koffs,
@@ -156,32 +158,56 @@ __global__ void __launch_bounds__(256) kmer_hash31_roll_kernel(
     const uint32_t K = (uint32_t)(__ldg(&koffs[q + 1]) - k0);
     const uint32_t i0 = (uint32_t)(t - __ldg(&ioffs[q])) * KPT;
     const uint32_t n = min((uint32_t)KPT, K - i0);
-    const char* s = seq + __ldg(&qoffs[q]) + i0;
-    const uint64_t mask = (1ULL << 62) - 1;
-    uint64_t fwd = 0, rc = 0;
+    // The 30 + n bases of this item, four at a time: aligned 32-bit loads re-aligned with a funnel shift,
+    // the four 2-bit codes of a word extracted in parallel (A0 C1 G2 T3 from bits 2..1 of the letter) and
+    // packed MSB-first with one multiply; a word is valid iff the table's letters for its codes equal it.
+    constexpr int NG = (30 + KPT + 3) / 4;  // groups of 4 bases
+    const uint64_t sbyte = __ldg(&qoffs[q]) + i0;
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(seq + (sbyte & ~3ULL));  // (the buffer is padded by 64 B)
+    const uint32_t sh = (uint32_t)(sbyte & 3ULL) * 8u;
+    uint32_t raw[NG + 1];
+#pragma unroll
+    for (int i = 0; i <= NG; i++) raw[i] = __ldg(wp + i);
+    const uint32_t valid_len = 30u + n;
+    uint64_t p_hi = 0;
+    uint32_t g_last = 0;
     bool bad = false;
 #pragma unroll
-    for (int i = 0; i < 30 + KPT; i++) {
-        if (i < 30 + (int)n) {
-            const uint32_t c = (uint8_t)__ldg(&s[i]);
-            const uint32_t x = (c >> 1) & 3u;
-            const uint32_t code = x ^ (x >> 1);  // A0 C1 G2 T3
-            bad |= ((0x54474341u >> (8 * code)) & 0xFFu) != c;
-            fwd = ((fwd << 2) | code) & mask;
-            rc = (rc >> 2) | ((uint64_t)(3u - code) << 60);
-            if (i >= 30) {
-                const uint64_t v = ((canonicalize && rc < fwd) ? rc : fwd) << 2;  // 31 bases + 1 pad = 8 groups of 4
-                uint64_t w[4];
+    for (int i = 0; i < NG; i++) {
+        const uint32_t w = __funnelshift_r(raw[i], raw[i + 1], sh);  // letters 4i .. 4i+3, first in the low byte
+        const uint32_t x = (w >> 1) & 0x03030303u;
+        const uint32_t code = x ^ ((x >> 1) & 0x01010101u);
+        const uint32_t g = (code * 0x40100401u) >> 24;             // c0<<6 | c1<<4 | c2<<2 | c3
+        const uint32_t nv = valid_len > 4u * i ? min(4u, valid_len - 4u * i) : 0u;
+        const uint32_t vm = nv >= 4u ? 0xFFFFFFFFu : ((1u << (8u * nv)) - 1u);
+        bad |= ((lut[g] ^ w) & vm) != 0u;
+        if (i < 8) p_hi |= (uint64_t)g << (56 - 8 * i);
+        else g_last = g;
+    }
+    if (bad) {
+        report_bad(err, q);
+        return;
+    }
+    const uint64_t mask = (1ULL << 62) - 1;
 #pragma unroll
-                for (int j = 0; j < 4; j++)
-                    w[j] = (uint64_t)lut[(v >> (56 - 16 * j)) & 0xFF] | ((uint64_t)lut[(v >> (48 - 16 * j)) & 0xFF] << 32);
-                w[3] &= 0x00FFFFFFFFFFFFFFULL;  // drop the pad letter
-                const uint64_t g = k0 + i0 + (uint32_t)(i - 30);
-                for (uint32_t j = 0; j < num_hashes; j++) hashes[(uint64_t)j * total_kmers + g] = xxh64_packed(w, 31, j);
-            }
+    for (int m = 0; m < KPT; m++) {
+        if (m < (int)n) {
+            const uint64_t win = m == 0 ? p_hi : ((p_hi << (2 * m)) | ((uint64_t)g_last >> (8 - 2 * m)));  // bases m .. m+31
+            const uint64_t fwd = win >> 2;                                                                  // bases m .. m+30
+            // reverse complement: complement every 2-bit code, reverse the order of the 31 codes
+            uint64_t r = __brevll(~fwd & mask);
+            r = ((r >> 1) & 0x5555555555555555ULL) | ((r & 0x5555555555555555ULL) << 1);
+            const uint64_t rc = r >> 2;
+            const uint64_t v = ((canonicalize && rc < fwd) ? rc : fwd) << 2;  // 31 bases + 1 pad = 8 groups of 4
+            uint64_t w[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                w[j] = (uint64_t)lut[(v >> (56 - 16 * j)) & 0xFF] | ((uint64_t)lut[(v >> (48 - 16 * j)) & 0xFF] << 32);
+            w[3] &= 0x00FFFFFFFFFFFFFFULL;  // drop the pad letter
+            const uint64_t g = k0 + i0 + (uint32_t)m;
+            for (uint32_t j = 0; j < num_hashes; j++) hashes[(uint64_t)j * total_kmers + g] = xxh64_packed(w, 31, j);
         }
     }
-    if (bad) report_bad(err, q);
 }
 
 // rule fix_query on the bases (Snakefile:326-332: `seqtk seq -U` + awk gsub(/[^ACGT]/,"A")): 16 bytes
