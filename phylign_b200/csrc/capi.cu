@@ -798,19 +798,32 @@ extern "C" int phy_merged_fetch(phy_ctx* ctx, phy_merged** out) {
     if (!m) return PHY_ERR_NOMEM;
     m->n_queries = ctx->nq;
     const bool holder = ctx->n_ranks == 1 || ctx->rank == 0 || ctx->merge_sharded;
-    const uint64_t n = holder ? ctx->n_final : 0;
     m->offs = (uint64_t*)result_alloc(ctx, ((size_t)ctx->nq + 1) * sizeof(uint64_t));
-    m->cands = (phy_cand*)result_alloc(ctx, std::max<uint64_t>(1, n) * sizeof(phy_cand));
-    if (m->offs) memset(m->offs, 0, ((size_t)ctx->nq + 1) * sizeof(uint64_t));
-    if (!m->offs || !m->cands) {
+    if (!m->offs) {
         phy_merged_free(m);
         phy_set_error(ctx, "host memory exhausted");
         return PHY_ERR_NOMEM;
     }
+    memset(m->offs, 0, ((size_t)ctx->nq + 1) * sizeof(uint64_t));
     int rc = PHY_OK;
-    if (holder) {
-        rc = phy_d2h(ctx, m->offs, ctx->d_foffs.p, ((size_t)ctx->nq + 1) * sizeof(uint64_t));
-        if (rc == PHY_OK && n) rc = phy_d2h(ctx, m->cands, ctx->d_final.p, n * sizeof(phy_cand));
+    if (holder) rc = phy_d2h(ctx, m->offs, ctx->d_foffs.p, ((size_t)ctx->nq + 1) * sizeof(uint64_t));
+    if (rc == PHY_OK) rc = cudaStreamSynchronize(ctx->stream) == cudaSuccess ? PHY_OK : PHY_ERR_CUDA;
+    // the exact number of kept candidates is the last offset (ctx->n_final is only the bound the device
+    // buffers were sized with)
+    const uint64_t n = (holder && rc == PHY_OK) ? m->offs[ctx->nq] : 0;
+    if (n > ctx->n_final) {
+        phy_merged_free(m);
+        phy_set_error(ctx, "internal: merged list longer than its bound");
+        return PHY_ERR_STATE;
+    }
+    if (rc == PHY_OK) {
+        m->cands = (phy_cand*)result_alloc(ctx, std::max<uint64_t>(1, n) * sizeof(phy_cand));
+        if (!m->cands) {
+            phy_merged_free(m);
+            phy_set_error(ctx, "host memory exhausted");
+            return PHY_ERR_NOMEM;
+        }
+        if (n) rc = phy_d2h(ctx, m->cands, ctx->d_final.p, n * sizeof(phy_cand));
     }
     if (rc != PHY_OK) {
         phy_merged_free(m);

@@ -187,6 +187,8 @@ void phy_nccl_shutdown(phy_ctx* ctx) {
 // merged lists stay distributed over the ranks (phy_merged_range tells which queries a rank holds), so
 // the merge work and the final download shrink with the number of GPUs.  "merge_mode" 0: rank 0
 // finalises every query.
+int phy_merge_segments_bounded(phy_ctx* ctx, uint32_t top_n, uint64_t max_total);
+
 int phy_nccl_merge(phy_ctx* ctx, uint32_t top_n) {
     const bool sharded = ctx->merge_sharded;
     ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
@@ -225,9 +227,10 @@ int phy_nccl_merge(phy_ctx* ctx, uint32_t top_n) {
         rank_totals_range_kernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(all.p, R, nq, q_lo, q_hi, ctx->d_qcount.p);
         ctx->launches++;
     }
-    uint64_t total = 0;
+    uint64_t total = 0;  // bound: every candidate of every rank (this rank's slice holds a part of them)
+    for (uint32_t r = 0; r < R; r++) total += bound(r, R);
     PHY_TRY(phy_ensure(ctx, ctx->d_qoffs_c, nq + 2));
-    PHY_TRY(phy_exscan(ctx, ctx->d_qcount.p, nq, ctx->d_qoffs_c.p, &total));
+    PHY_TRY(phy_exscan(ctx, ctx->d_qcount.p, nq, ctx->d_qoffs_c.p, nullptr));
     PHY_TRY(phy_ensure(ctx, ctx->d_ckey, total + 1));
     PHY_TRY(phy_ensure(ctx, ctx->d_cval, total + 1));
     if (q_hi > q_lo && total) {
@@ -239,5 +242,5 @@ int phy_nccl_merge(phy_ctx* ctx, uint32_t top_n) {
     }
     ctx->merged_q_lo = q_lo;
     ctx->merged_q_hi = q_hi;
-    return phy_merge_segments(ctx, top_n);
+    return phy_merge_segments_bounded(ctx, top_n, total);
 }

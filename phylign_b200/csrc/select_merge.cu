@@ -262,6 +262,8 @@ int phy_order_units(phy_ctx* ctx, uint64_t cells) {
     return PHY_OK;
 }
 
+int phy_merge_segments_bounded(phy_ctx* ctx, uint32_t top_n, uint64_t max_total);
+
 // candidates supplied by the host, already grouped per query (offs[nq+1])
 int phy_merge_host_impl(phy_ctx* ctx, uint32_t nq, uint32_t top_n, const uint64_t* offs, const phy_cand* cands) {
     const uint64_t total = offs[nq];
@@ -278,7 +280,7 @@ int phy_merge_host_impl(phy_ctx* ctx, uint32_t nq, uint32_t top_n, const uint64_
         ctx->launches++;
         PHY_CUDA(ctx, cudaGetLastError());
     }
-    return phy_merge_segments(ctx, top_n);
+    return phy_merge_segments_bounded(ctx, top_n, total);
 }
 
 // out must hold n+1 entries; *total_host receives out[n]
@@ -295,8 +297,10 @@ int phy_exscan(phy_ctx* ctx, const uint32_t* d_in, uint64_t n, uint64_t* d_out, 
         PHY_CUDA(ctx, cudaMemsetAsync(d_out, 0, sizeof(uint64_t), ctx->stream));
     }
     PHY_CUDA(ctx, cudaGetLastError());
-    PHY_CUDA(ctx, cudaMemcpyAsync(total_host, d_out + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-    PHY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (total_host) {  // callers that can size their buffers from a host-side bound pass nullptr: no host wait
+        PHY_CUDA(ctx, cudaMemcpyAsync(total_host, d_out + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        PHY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
     return PHY_OK;
 }
 
@@ -309,8 +313,11 @@ int phy_launch_sort_units(phy_ctx* ctx) {
     return PHY_OK;
 }
 
-// sort + cut the per-query candidate segments [d_qoffs_c] in (d_ckey, d_cval); compacts into d_final
-int phy_merge_segments(phy_ctx* ctx, uint32_t top_n) {
+// sort + cut the per-query candidate segments [d_qoffs_c] in (d_ckey, d_cval); compacts into d_final.
+// max_total = a host-side bound on the number of kept candidates (the number of candidates that went
+// in): the output is sized from it, so nothing here waits for the device -- the exact count is read
+// from d_foffs[nq] by phy_merged_fetch, which has to wait for the results anyway.
+int phy_merge_segments_bounded(phy_ctx* ctx, uint32_t top_n, uint64_t max_total) {
     const uint32_t nq = ctx->nq;
     PHY_TRY(phy_ensure(ctx, ctx->d_nfinal, nq + 1));
     PHY_TRY(phy_ensure(ctx, ctx->d_foffs, nq + 2));
@@ -319,29 +326,30 @@ int phy_merge_segments(phy_ctx* ctx, uint32_t top_n) {
                                                        ctx->d_cval.p, ctx->d_nfinal.p);
     ctx->launches++;
     PHY_CUDA(ctx, cudaGetLastError());
-    uint64_t total = 0;
-    PHY_TRY(phy_exscan(ctx, ctx->d_nfinal.p, nq, ctx->d_foffs.p, &total));
-    PHY_TRY(phy_ensure(ctx, ctx->d_final, total + 1));
-    if (total) {
+    PHY_TRY(phy_exscan(ctx, ctx->d_nfinal.p, nq, ctx->d_foffs.p, nullptr));
+    PHY_TRY(phy_ensure(ctx, ctx->d_final, max_total + 1));
+    if (max_total) {
         compact_final_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_qoffs_c.p, ctx->d_foffs.p, nq,
                                                              ctx->d_ckey.p, ctx->d_cval.p, ctx->d_final.p);
         ctx->launches++;
         PHY_CUDA(ctx, cudaGetLastError());
     }
-    ctx->n_final = total;
+    ctx->n_final = max_total;  // upper bound; exact = d_foffs[nq]
     return PHY_OK;
+}
+
+int phy_merge_segments(phy_ctx* ctx, uint32_t top_n) {
+    uint64_t total = 0;  // candidates that go in = qoffs_c[nq]
+    PHY_CUDA(ctx, cudaMemcpyAsync(&total, ctx->d_qoffs_c.p + ctx->nq, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    PHY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return phy_merge_segments_bounded(ctx, top_n, total);
 }
 
 int phy_launch_merge(phy_ctx* ctx, uint32_t top_n) {
     const uint32_t nq = ctx->nq;
     PHY_TRY(phy_ensure(ctx, ctx->d_qoffs_c, nq + 2));
-    uint64_t total = 0;
-    PHY_TRY(phy_exscan(ctx, ctx->d_qcount.p, nq, ctx->d_qoffs_c.p, &total));
-    if (total != ctx->n_hits) {
-        phy_set_error(ctx, "internal: candidate count mismatch (%llu vs %llu)", (unsigned long long)total,
-                      (unsigned long long)ctx->n_hits);
-        return PHY_ERR_STATE;
-    }
+    const uint64_t total = ctx->n_hits;  // every kept hit is a candidate: qcount sums to n_hits (no host wait)
+    PHY_TRY(phy_exscan(ctx, ctx->d_qcount.p, nq, ctx->d_qoffs_c.p, nullptr));
     PHY_TRY(phy_ensure(ctx, ctx->d_ckey, total + 1));
     PHY_TRY(phy_ensure(ctx, ctx->d_cval, total + 1));
     PHY_TRY(phy_ensure(ctx, ctx->d_qcursor, nq + 1));
@@ -354,5 +362,5 @@ int phy_launch_merge(phy_ctx* ctx, uint32_t top_n) {
         ctx->launches++;
         PHY_CUDA(ctx, cudaGetLastError());
     }
-    return phy_merge_segments(ctx, top_n);
+    return phy_merge_segments_bounded(ctx, top_n, total);
 }
