@@ -707,9 +707,28 @@ def expected_file_digests(m, records, res, mowner, names_in_rank_order, refs_by_
     return out, fa
 
 
+def wait_gpus_released(n_gpus, timeout_s=20.0):
+    """Set-up hygiene between one-shot runs: the previous holder of ~90 GB of HBM (this process' closed
+    context, or the match-db run before) may still be tearing down; a CUDA context created meanwhile
+    can take seconds instead of 0.3 s.  Wait until the driver reports the memory as free."""
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < timeout_s:
+        try:
+            out = subprocess.run(["nvidia-smi", "--query-gpu=memory.used", "--format=csv,noheader,nounits"],
+                                 capture_output=True, text=True, timeout=10).stdout.split()
+            used = [float(x) for x in out[:n_gpus]]
+            if used and max(used) < 8000:       # MiB (this process keeps a small context of its own)
+                break
+        except Exception:
+            break
+        time.sleep(0.25)
+    return time.perf_counter() - t0
+
+
 def run_match_db(workdir, tag, fasta, n_gpus, bases, hbm_budget_gb=0, extra=()):
     """One files-in -> files-out run of the product CLI; returns the e2e_files record."""
     import gzip
+    waited = wait_gpus_released(n_gpus)
     outdir = os.path.join(workdir, f"out_{tag}")
     tj = os.path.join(workdir, f"timing_{tag}.json")
     cmd = [sys.executable, "-m", "phylign_b200.cli", "match-db", "--cobs-dir", os.path.join(workdir, "cobs"),
@@ -742,7 +761,7 @@ def run_match_db(workdir, tag, fasta, n_gpus, bases, hbm_budget_gb=0, extra=()):
     got_fa = hashlib.sha256(open(fa_path, "rb").read()).hexdigest()
     ph = timing["phases_s"]
     host_s = timing["total_s"] - ph.get("index_load_wait_s", 0.0) - ph.get("gpu_match_s", 0.0)
-    rec = {"value": bases / wall, "unit": UNIT, "wall_s": round(wall, 3),
+    rec = {"value": bases / wall, "unit": UNIT, "wall_s": round(wall, 3), "waited_for_free_hbm_s": round(waited, 2),
            "command": "python -m phylign_b200.cli match-db --cobs-dir DIR --batches FILE -q reads.fa --match-dir 03_match "
                       "--filter-out 04_filter/reads.fa -t 0.7 -n 100" + (f" --gpus {n_gpus}" if n_gpus > 1 else ""),
            "after_index_load": {"value": bases / max(1e-9, timing["total_s"] - ph.get("index_load_wait_s", 0.0) - ph.get("plan_s", 0.0)),
