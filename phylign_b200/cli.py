@@ -108,9 +108,21 @@ def cmd_cobs_query(a):
 
 
 # ------------------------------------------------------------------------------------ filter
+def _fixed_width(buf: np.ndarray, off: np.ndarray, ln: np.ndarray, width: int = 0) -> np.ndarray:
+    """Substrings buf[off[i] : off[i]+ln[i]] as one NUL-padded fixed-width bytes array (dtype S<width>),
+    gathered with numpy -- no per-string Python objects."""
+    if len(off) == 0:
+        return np.zeros(0, dtype=f"S{max(1, width)}")
+    width = max(width, int(ln.max()), 1)
+    cols = np.arange(width, dtype=np.int64)
+    idx = np.minimum(off[:, None] + cols[None, :], len(buf) - 1)
+    mat = np.where(cols[None, :] < ln[:, None], buf[idx], 0).astype(np.uint8)
+    return np.ascontiguousarray(mat).view(f"S{width}").ravel()
+
+
 def parse_match_file_native(path):
     """A match file parsed with the rules of filter_queries.py:27-66 by the library's C++ parser, as arrays:
-    (qnames [str per block], first_hit uint64[n_blocks+1], ref_ids int64[n_hits], refs_sorted [str],
+    (qnames S-array per block, first_hit uint64[n_blocks+1], ref_ids int64[n_hits], refs_sorted [str],
     kmers uint32[n_hits]); ref_ids index refs_sorted (byte order = Python str order for ASCII)."""
     import ctypes as C
     from . import _lib
@@ -132,20 +144,42 @@ def parse_match_file_native(path):
         kmers = arr(m.kmers, nh, np.uint32)
     finally:
         L.phy_match_text_free(mp)
-    qnames = [text[o:o + n].decode() for o, n in zip(q_off.tolist(), q_len.tolist())]
+    buf = np.frombuffer(text, dtype=np.uint8)
+    qnames = _fixed_width(buf, q_off, q_len)
     if nh:
-        width = int(ref_len.max())
-        buf = np.frombuffer(text, dtype=np.uint8)
-        cols = np.arange(width, dtype=np.int64)
-        idx = np.minimum(ref_off[:, None] + cols[None, :], len(buf) - 1)
-        mat = np.where(cols[None, :] < ref_len[:, None], buf[idx], 0).astype(np.uint8)
-        names = np.ascontiguousarray(mat).view(f"S{width}").ravel()     # NUL padded fixed-width strings
-        uniq, inv = np.unique(names, return_inverse=True)
+        uniq, inv = np.unique(_fixed_width(buf, ref_off, ref_len), return_inverse=True)
         refs_sorted = [u.decode() for u in uniq.tolist()]
         ref_ids = inv.astype(np.int64)
     else:
         refs_sorted, ref_ids = [], np.zeros(0, np.int64)
     return qnames, first_hit, ref_ids, refs_sorted, kmers
+
+
+class _QueryNameIndex:
+    """Query name -> position in the query file, for whole arrays of names at once.  The usual match
+    file lists the queries of the query file in order: that case is one array comparison."""
+
+    def __init__(self, qid: dict):
+        names = [None] * len(qid)
+        for n, i in qid.items():
+            names[i] = n.encode()
+        self.width = max([len(n) for n in names] + [1])
+        self.names = np.array(names, dtype=f"S{self.width}") if names else np.zeros(0, dtype="S1")
+        self.order = np.argsort(self.names, kind="stable")
+        self.sorted = self.names[self.order]
+
+    def lookup(self, qnames: np.ndarray, what: str) -> np.ndarray:
+        if len(qnames) == len(self.names) and qnames.dtype.itemsize <= self.width and \
+                bool((qnames.astype(self.names.dtype) == self.names).all()):
+            return np.arange(len(self.names), dtype=np.int64)
+        q = qnames.astype(f"S{max(self.width, qnames.dtype.itemsize)}")
+        srt = self.sorted.astype(q.dtype)
+        pos = np.minimum(np.searchsorted(srt, q), max(len(srt) - 1, 0))
+        ok = (srt[pos] == q) if len(srt) else np.zeros(len(q), bool)
+        if not bool(ok.all()):
+            bad = q[~ok][0].decode(errors="replace")
+            raise KeyError(f"query {bad!r} of {what} is not in the query file")
+        return self.order[pos].astype(np.int64)
 
 
 def _load_filter_queries(query_fn):
@@ -161,21 +195,21 @@ def _parsed_pieces(match_fns, qid, brank, log):
     Files are parsed natively (phy_parse_match_text); several files of one batch are allowed."""
     from .matcher import CAND_DT
     by_batch = {}
-    for fn in match_fns:
+    with ThreadPoolExecutor(max_workers=min(16, max(1, len(match_fns)))) as ex:   # gunzip + C++ parser release the GIL
+        parsed_files = list(ex.map(parse_match_file_native, match_fns))
+    for fn, parsed_one in zip(match_fns, parsed_files):
         batch = os.path.basename(fn).split("____")[0]
         print(f"Translating matches {fn}", file=log)
-        by_batch.setdefault(batch, []).append(parse_match_file_native(fn))
+        by_batch.setdefault(batch, []).append(parsed_one)
     pieces, refs_by_rank = [], {}
+    qindex = _QueryNameIndex(qid)
     for batch, parsed in by_batch.items():
         br = brank[batch]
         refs = sorted({r for p in parsed for r in p[3]})          # accessions of the batch, str order
         rr = {r: i for i, r in enumerate(refs)}
         refs_by_rank[br] = refs
         for qnames, first_hit, ref_ids, refs_sorted, kmers in parsed:
-            try:
-                q_of_block = np.array([qid[q] for q in qnames], dtype=np.int64)
-            except KeyError as e:
-                raise KeyError(f"query {e.args[0]!r} of batch {batch} is not in the query file") from None
+            q_of_block = qindex.lookup(qnames, f"batch {batch}")
             remap = np.array([rr[r] for r in refs_sorted], dtype=np.int64)   # file-local id -> batch rank
             rank = remap[ref_ids] if len(ref_ids) else np.zeros(0, np.int64)
             c = np.zeros(len(kmers), dtype=CAND_DT)

@@ -327,7 +327,7 @@ def test_native_match_file_parser_equals_python_parser(tmp_path):
             p = os.path.join(H.GOLDEN, f"n{keep}", f"{b}____queries.gz")
             want = parse_match_file(p)
             qnames, first_hit, ref_ids, refs_sorted, kmers = parse_match_file_native(p)
-            assert qnames == [q for q, _ in want]
+            assert [q.decode() for q in qnames.tolist()] == [q for q, _ in want]
             got = [[(refs_sorted[int(r)], int(k)) for r, k in zip(ref_ids[int(a):int(z)], kmers[int(a):int(z)])]
                    for a, z in zip(first_hit[:-1], first_hit[1:])]
             assert got == [hits for _, hits in want]
@@ -346,7 +346,22 @@ def test_native_match_file_parser_equals_python_parser(tmp_path):
     ok.write_text("\n*q1 some comment\t2  \n  x_R1 \t 5\r\ny_R0\t4\n\n*q2\t0\n")
     assert parse_match_file(str(ok)) == [("q1", [("R1", 5), ("R0", 4)]), ("q2", [])]
     qn, fh, ri, rs, km = parse_match_file_native(str(ok))
-    assert qn == ["q1", "q2"] and fh.tolist() == [0, 2, 2] and [rs[i] for i in ri] == ["R1", "R0"] and km.tolist() == [5, 4]
+    assert qn.tolist() == [b"q1", b"q2"] and fh.tolist() == [0, 2, 2] and [rs[i] for i in ri] == ["R1", "R0"] and km.tolist() == [5, 4]
+
+
+def test_query_name_index_vectorised_lookup():
+    """Names of match-file blocks -> positions in the query file: in-order fast path, any order, unknown names."""
+    from phylign_b200.cli import _QueryNameIndex
+    qid = {"q1": 0, "longer_name_7": 1, "b": 2}
+    ix = _QueryNameIndex(qid)
+    assert ix.lookup(np.array([b"q1", b"longer_name_7", b"b"]), "x").tolist() == [0, 1, 2]
+    assert ix.lookup(np.array([b"b", b"q1", b"b"], dtype="S2"), "x").tolist() == [2, 0, 2]
+    assert ix.lookup(np.zeros(0, dtype="S1"), "x").tolist() == []
+    with pytest.raises(KeyError):
+        ix.lookup(np.array([b"q1", b"nope"]), "batch zz__01")
+    with pytest.raises(KeyError):
+        ix.lookup(np.array([b"q1", b"longer_name_7_and_more", b"b"]), "x")
+    assert _QueryNameIndex({}).lookup(np.zeros(0, dtype="S1"), "x").tolist() == []
 
 
 def _fake_results(rnd, nq, idx_ids, n_docs, recs):
