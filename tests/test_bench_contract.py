@@ -83,3 +83,19 @@ def test_digest_helpers_are_placement_independent():
     cands = np.array([(9, 0, 0, 0), (8, 0, 1, 1), (7, 1, 0, 0)], CAND_DT)
     fo, fc = bench.full_merged(FakeDist(), FakeM(), offs, cands)
     assert fo.tolist() == [0, 2, 3, 4, 6] and fc["score"].tolist() == [9, 8, 7, 5, 4, 4]
+
+
+def test_reference_arm_prefers_a_cobs_binary_on_path(tmp_path):
+    """when an executable `cobs` is on PATH the CPU arm times IT (kind "reference"), for the
+    query leg and inside the file pipeline.  Exercised with tests/fake_cobs.py (the oracle CLI posing as cobs)."""
+    import oracle
+    oracle.build()
+    os.symlink(os.path.join(ROOT, "tests", "fake_cobs.py"), tmp_path / "cobs")
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", ORC_CLI=oracle.CLI_PATH, PATH=f"{tmp_path}{os.pathsep}{os.environ['PATH']}")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--reads", "60",
+                        "--read-len", "150", "--indexes", "2", "--docs", "64", "--genome-len", "2000",
+                        "--steps", "1", "--warmup", "1"], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cobs_on_path"] == str(tmp_path / "cobs")
+    assert d["e2e_files"]["cobs_binary"] == str(tmp_path / "cobs") and d["value"] > 0
