@@ -2,7 +2,14 @@
 """Generate tests/golden/* by running the UNMODIFIED reference scripts.
 
 Run in the build container only (needs /root/reference):
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [--with-cobs]
+
+--with-cobs: when an executable `cobs` (COBS 0.2.1, envs/cobs.yaml:5) is on PATH or in
+$PHYLIGN_REAL_COBS, the three indexes are ALSO built with `cobs classic-construct` and must equal the
+oracle's byte for byte, and the <batch>.cobs.txt.gz texts are taken from the real
+`cobs query --load-complete -t 0.7 -T 2 -i ... -f ...` (run_cobs_streaming.sh:24-29; equal-score lines
+put in document order, which cobs leaves undefined).  PROVENANCE.json records which producer wrote the
+vectors, so "parity unpinned" can be dropped from the docs the day this has run.
 
 What is produced (all small, committed):
   xxh64_kat.json            XXH64 known answers from python-xxhash AND libxxhash
@@ -108,7 +115,45 @@ def xxh64_kats():
     return vecs
 
 
+def real_cobs():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_real_cobs import real_cobs as find
+    return find()
+
+
+def cobs_construct(cobs, names, docs):
+    """`cobs classic-construct` over one FASTA per document (file stem = document name)."""
+    with tempfile.TemporaryDirectory() as td:
+        ddir = os.path.join(td, "docs")
+        os.makedirs(ddir)
+        for n, s in zip(names, docs):
+            with open(os.path.join(ddir, n + ".fa"), "w") as f:
+                f.write(f">{n}\n{s.decode()}\n")
+        out = os.path.join(td, "built.cobs_classic")
+        base = [cobs, "classic-construct", "-k", "31", "--num-hashes", "1", "--false-positive-rate", "0.3"]
+        for variant in (["--clobber"], []):
+            r = subprocess.run(base + variant + [ddir, out], capture_output=True, text=True)
+            if r.returncode == 0 and os.path.exists(out):
+                return open(out, "rb").read()
+        raise SystemExit("cobs classic-construct failed: " + r.stderr[-500:])
+
+
+def canonical_tie_order(text, names):
+    """cobs text with the equal-score lines of every block in document order."""
+    from oracle import filters
+    pos = {n: i for i, n in enumerate(names)}
+    out = []
+    for head, n, hits in filters.parse_cobs_text(text):
+        out.append(f"*{head}\t{n}\n")
+        out.extend(f"{nm}\t{sc}\n" for nm, sc in sorted(hits, key=lambda x: (-x[1], pos[x[0]])))
+    return "".join(out)
+
+
 def main():
+    with_cobs = "--with-cobs" in sys.argv
+    cobs = real_cobs() if with_cobs else None
+    if with_cobs and not cobs:
+        raise SystemExit("--with-cobs: no `cobs` executable on PATH and $PHYLIGN_REAL_COBS unset")
     oracle.build()
     with open(os.path.join(HERE, "xxh64_kat.json"), "w") as f:
         json.dump(xxh64_kats(), f, indent=0)
@@ -141,6 +186,11 @@ def main():
             p = os.path.join(td, "i.cobs_classic")
             idx.write(p)
             raw = open(p, "rb").read()
+            if cobs:
+                built = cobs_construct(cobs, doc_names(bi, n_docs), docs)
+                if built != raw:
+                    raise SystemExit(f"{batch}: `cobs classic-construct` output differs from the oracle's index "
+                                     f"({len(built)} vs {len(raw)} bytes): fix the oracle (SURVEY Appendix A.1/A.10)")
             with lzma.open(os.path.join(HERE, f"{batch}.cobs_classic.xz"), "wb", preset=6) as f:
                 f.write(raw)
             # the CLI and the python binding must agree
@@ -149,6 +199,20 @@ def main():
                  "-i", p, "-f", os.path.join(HERE, "queries.fa")]).decode()
         txt = idx.query_text([(n, s.encode()) for n, s in queries], THRESHOLD)
         assert txt == txt_cli
+        if cobs:        # the vector comes from the real binary; the oracle must agree on everything it defines
+            with tempfile.TemporaryDirectory() as td:
+                p = os.path.join(td, "i.cobs_classic")
+                open(p, "wb").write(raw)
+                qok = os.path.join(td, "q.fa")       # (records shorter than k are an open item: test_real_cobs.py)
+                with open(qok, "w") as f:
+                    f.write("".join(f">{n}\n{s}\n" for n, s in queries if len(s) >= 31))
+                real = subprocess.run([cobs, "query", "--load-complete", "-t", str(THRESHOLD), "-T", "2", "-i", p, "-f", qok],
+                                      check=True, stdout=subprocess.PIPE).stdout.decode()
+            names = doc_names(bi, n_docs)
+            want = canonical_tie_order(idx.query_text([(n, s.encode()) for n, s in queries if len(s) >= 31], THRESHOLD), names)
+            if canonical_tie_order(real, names) != want:
+                raise SystemExit(f"{batch}: `cobs query` output differs from the oracle's: run tests/test_real_cobs.py "
+                                 f"for the item-by-item diagnosis")
         with gzip.GzipFile(os.path.join(HERE, f"{batch}.cobs.txt.gz"), "wb", mtime=0) as f:
             f.write(txt.encode())
 
@@ -177,6 +241,12 @@ def main():
                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True, env=env).stdout
         with open(os.path.join(od, "queries.fa"), "wb") as f:
             f.write(fa)
+    with open(os.path.join(HERE, "PROVENANCE.json"), "w") as f:
+        json.dump({"cobs_text_and_indexes": ("real cobs binary: " + cobs + " (indexes byte-identical to the oracle's, query text "
+                                             "identical up to the order of equal-score lines)") if cobs else
+                   "oracle/cobs_oracle.c (parity with the real cobs binary UNPINNED: cobs not installable offline)",
+                   "postprocess_and_filter_outputs": "unmodified /root/reference/scripts/postprocess_cobs.py and filter_queries.py, executed"},
+                  f, indent=1)
     print("golden vectors written to", HERE)
 
 
