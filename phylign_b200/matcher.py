@@ -112,17 +112,31 @@ class _SerializedLib:
     round's indexes between the match calls of the main thread."""
 
     def __init__(self, L, lock):
-        self._L, self._lock = L, lock
+        self._L, self._lock, self._errors = L, lock, {}
 
     def __getattr__(self, name):
+        import threading
         fn = getattr(self._L, name)
-        lock = self._lock
+        lock, L, errs = self._lock, self._L, self._errors
 
         def call(*args):
             with lock:
-                return fn(*args)
+                rc = fn(*args)
+                # a failing call on a context handle: read its message before another thread's call replaces it
+                if isinstance(rc, int) and rc < 0 and args and isinstance(args[0], C.c_void_p) and args[0].value:
+                    try:
+                        msg = L.phy_last_error(args[0])
+                        errs[threading.get_ident()] = msg.decode() if msg else ""
+                    except Exception:
+                        pass
+                return rc
         setattr(self, name, call)
         return call
+
+    def take_error(self):
+        """The message captured with this thread's last failing call (None when there is none)."""
+        import threading
+        return self._errors.pop(threading.get_ident(), None)
 
 
 class Matcher:
@@ -162,6 +176,10 @@ class Matcher:
             pass
 
     def _ck(self, code):
+        if code != _lib.PHY_OK:
+            msg = self._L.take_error()
+            if msg is not None:
+                raise _lib.PhylignCudaError(code, msg)
         _lib.check(code, self._ctx)
 
     # ------------------------------------------------------------------ index store
