@@ -32,7 +32,7 @@ bool read_file(const char* path, std::vector<char>& buf) {
     if (fd < 0) return false;
     struct stat st;
     size_t hint = (fstat(fd, &st) == 0 && S_ISREG(st.st_mode)) ? (size_t)st.st_size : 0;
-    buf.resize(hint ? hint : (1u << 20));
+    buf.resize(hint ? hint + 1 : (1u << 20));  // +1: the read that reports EOF needs no regrowth
     size_t n = 0;
     for (;;) {
         if (n == buf.size()) buf.resize(buf.size() * 2);
