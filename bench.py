@@ -764,9 +764,14 @@ def run_match_db(workdir, tag, fasta, n_gpus, bases, hbm_budget_gb=0, extra=()):
                                                             "MASTER_ADDR", "MASTER_PORT", "GROUP_RANK", "ROLE_RANK")}
     env["PYTHONPATH"] = ROOT + os.pathsep + env.get("PYTHONPATH", "")
     t0 = time.perf_counter()
-    r = subprocess.run(cmd, env=env, capture_output=True, text=True, cwd=ROOT)
+    try:        # a stuck run must not cost the bench line (the workers of --gpus N end with their parent)
+        r = subprocess.run(cmd, env=env, capture_output=True, text=True, cwd=ROOT, timeout=900)
+    except subprocess.TimeoutExpired:
+        shutil.rmtree(outdir, ignore_errors=True)
+        return {"value": None, "error": "match-db did not finish within 900 s"}, None
     wall = time.perf_counter() - t0
     if r.returncode != 0:
+        shutil.rmtree(outdir, ignore_errors=True)
         return {"value": None, "error": r.stderr[-800:]}, None
     timing = json.load(open(tj))
     mdir = os.path.join(outdir, "03_match")

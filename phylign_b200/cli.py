@@ -294,8 +294,10 @@ def _spawn_match_db_workers(a):
     outside ACGT ...) takes the others down, which would otherwise block forever inside a
     collective waiting for it; the job then exits non-zero (`set -euo pipefail` callers)."""
     import shutil
+    import signal
     import subprocess
     import tempfile
+    import threading
     import time
     if a.filter_out:                           # parts of an earlier, interrupted run must not be joined
         import glob
@@ -305,6 +307,13 @@ def _spawn_match_db_workers(a):
     id_file = os.path.join(tmpdir, "id")
     argv = [x for x in sys.argv[1:]]
     procs = []
+
+    def _stop(signum, _frame):                 # a cancelled job (snakemake, scancel, ^C) takes its workers along
+        raise SystemExit(128 + signum)
+    old_handlers = {}
+    if threading.current_thread() is threading.main_thread():
+        for sg in (signal.SIGTERM, signal.SIGINT, signal.SIGHUP):
+            old_handlers[sg] = signal.signal(sg, _stop)
     try:
         for r in range(a.gpus):
             env = dict(os.environ, PHYLIGN_RANK=str(r), PHYLIGN_WORLD=str(a.gpus), PHYLIGN_NCCL_ID_FILE=id_file)
@@ -341,7 +350,27 @@ def _spawn_match_db_workers(a):
         for p in procs:
             if p.poll() is None:
                 p.kill()
+        for p in procs:
+            p.wait()
         shutil.rmtree(tmpdir, ignore_errors=True)
+        for sg, h in old_handlers.items():
+            signal.signal(sg, h)
+
+
+def _die_with_parent():
+    """Worker side of `match-db --gpus N`: SIGTERM when the supervising parent goes away without being
+    able to stop its workers (SIGKILL, OOM killer) -- an orphan would sit in an NCCL collective holding
+    its GPU.  Linux prctl(PR_SET_PDEATHSIG); a no-op where prctl is missing."""
+    import ctypes
+    import signal
+    parent = os.getppid()
+    try:
+        libc = ctypes.CDLL(None, use_errno=True)
+        libc.prctl(1, int(signal.SIGTERM), 0, 0, 0)       # PR_SET_PDEATHSIG = 1
+    except (OSError, AttributeError):
+        return
+    if os.getppid() != parent:                 # the parent died before prctl took effect
+        raise SystemExit(143)
 
 
 def _join_parts(final_path, parts):
@@ -431,6 +460,7 @@ def cmd_match_db(a):
         return _spawn_match_db_workers(a)
     nccl = a.gpus > 1 and rank >= 0          # worker of a multi-GPU job: candidate lists meet over NCCL
     if nccl:                                 # the workers share the host's cores
+        _die_with_parent()
         a.load_workers = max(2, a.load_workers // world)
         if not a.write_threads:
             from .match_files import default_threads

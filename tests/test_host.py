@@ -603,3 +603,62 @@ def test_native_reader_equals_python_reader_on_random_text(tmp_path):
         assert got == want, (case, txt)
         assert q.n == len(want) and q.total_bases == sum(len(s) for _, s in want)
         assert q.names() == [h.split(" ")[0] for h, _ in want]
+
+
+_FAKE_WORKERS = r"""
+import os, subprocess, sys
+sys.path.insert(0, {root!r})
+import phylign_b200.cli as cli
+real = subprocess.Popen
+worker = ("import os, sys, time; sys.path.insert(0, %r); import phylign_b200.cli as c; c._die_with_parent(); "
+          "open(os.environ['PIDF'] + '.' + os.environ['PHYLIGN_RANK'], 'w').write(str(os.getpid())); time.sleep(120)" % {root!r})
+subprocess.Popen = lambda cmd, env=None: real([sys.executable, "-c", worker], env=env)
+sys.argv = ["cli", "match-db", "--cobs-dir", "x", "--batches", "x", "-q", "x", "--match-dir", "x", "--gpus", "2"]
+cli.main()
+"""
+
+
+def _alive(pid):
+    try:
+        with open(f"/proc/{pid}/stat") as f:
+            return f.read().split(")")[-1].split()[0] != "Z"
+    except OSError:
+        return False
+
+
+def _run_fake_job(tmp_path, sig):
+    """Parent of `match-db --gpus 2` with stand-in workers (sleepers that call _die_with_parent), hit by `sig`."""
+    import signal
+    import subprocess
+    import sys
+    import time
+    pidf = str(tmp_path / "pid")
+    p = subprocess.Popen([sys.executable, "-c", _FAKE_WORKERS.format(root=ROOT)], env=dict(os.environ, PIDF=pidf))
+    deadline = time.time() + 60
+    while not (os.path.exists(pidf + ".0") and os.path.exists(pidf + ".1")
+               and open(pidf + ".0").read() and open(pidf + ".1").read()):
+        assert time.time() < deadline and p.poll() is None, "workers did not start"
+        time.sleep(0.05)
+    pids = [int(open(f"{pidf}.{r}").read()) for r in (0, 1)]
+    assert all(_alive(w) for w in pids)
+    p.send_signal(sig)
+    rc = p.wait(timeout=30)
+    deadline = time.time() + 10
+    while any(_alive(w) for w in pids) and time.time() < deadline:
+        time.sleep(0.05)
+    return rc, [w for w in pids if _alive(w)]
+
+
+def test_match_db_gpus_cancelled_parent_takes_its_workers_along(tmp_path):
+    """SIGTERM to the supervising parent (a cancelled snakemake job) must not leave workers behind holding
+    their GPUs inside a collective."""
+    import signal
+    rc, left = _run_fake_job(tmp_path, signal.SIGTERM)
+    assert rc == 128 + signal.SIGTERM and not left
+
+
+def test_match_db_gpus_workers_die_with_a_killed_parent(tmp_path):
+    """SIGKILL gives the parent no chance to clean up: the workers' PR_SET_PDEATHSIG ends them."""
+    import signal
+    rc, left = _run_fake_job(tmp_path, signal.SIGKILL)
+    assert rc == -signal.SIGKILL and not left
